@@ -1,0 +1,139 @@
+/*
+ * magicdrive_b200 — C ABI of the B200-native multi-view denoising hot path.
+ *
+ * Every entry point takes raw device pointers, sizes, strides and a cudaStream_t (as void*), returns 0 on
+ * success or a negative status, and never allocates, synchronises or takes ownership.  mdb_last_error()
+ * returns a thread-local message for the last failure.  Activations are bf16, channel-innermost (NHWC for
+ * feature maps == [tokens, channels] for transformer blocks); accumulation is fp32.
+ *
+ * The reference has no native boundary of its own for this path except one op: xformers'
+ * efficient_attention_forward_cutlass (third_party/xformers/xformers/csrc/attention/attention.cpp:27,
+ * attention_forward_generic.cu:330-334).  Everything else it runs is a torch.nn call; each function below
+ * names the reference call site (file:line under /root/reference) it replaces.
+ */
+#ifndef MAGICDRIVE_B200_H
+#define MAGICDRIVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_OK 0
+#define MDB_ERR_INVALID (-1)
+#define MDB_ERR_CUDA (-2)
+#define MDB_ERR_UNSUPPORTED (-3)
+
+const char* mdb_last_error(void);
+int mdb_version(void);
+/* 1 if a CUDA device of compute capability 10.x is usable, else 0 (never raises). */
+int mdb_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * mdb_gemm_conv: tensor-core (tcgen05) GEMM / implicit-GEMM convolution with fused epilogue.
+ *   out[pix, n] = scale * ( sum_{r,s,c} A[pix*stride + (r,s) - pad, c] * W[n, (r*taps_w+s)*C + c]
+ *                           + bias[n] + rowbias[img(pix), n] ) + residual[pix, n]
+ *   epi_mode 1 (GEGLU): W/bias are packed per 256-column tile as [128 value | 128 gate] and
+ *   out[pix, j] = value_j * gelu(gate_j) with n_out/2 output columns.
+ * Replaces: nn.Conv2d 3x3/1x1 in ResnetBlock2D (diffusers/models/resnet.py:537,560,586), Downsample2D
+ * (resnet.py:199), Upsample2D.conv (resnet.py:129), Transformer2DModel.proj_in/proj_out
+ * (transformer_2d.py:149,205), Attention.to_q/to_k/to_v/to_out (attention_processor.py:141-156),
+ * GEGLU.proj + FeedForward out (attention.py:270,226), connector (magicdrive/networks/blocks.py:83),
+ * ControlNet zero convs (magicdrive/networks/unet_addon_rawbox.py:221-272).
+ * A may be split over two sources along channels (torch.cat skip connections, unet_2d_blocks.py:1984,2086).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a0;      /* bf16 [n_img, h_in, w_in, lda0] using the first c0 channels */
+  const void* a1;      /* optional second source (NULL if c1 == 0) */
+  int c0, lda0, c1, lda1;
+  int n_img, h_in, w_in;
+  const void* w;       /* bf16 [n_out, taps_h*taps_w*(c0+c1)] */
+  int n_out;
+  int taps_h, taps_w, stride, pad_h, pad_w;
+  int h_out, w_out;
+  const float* bias;    /* [n_out] or NULL */
+  const float* rowbias; /* [n_img, rowbias_ld] or NULL */
+  int rowbias_ld;
+  const void* residual; /* bf16 [pixels, ldr] or NULL */
+  int ldr;
+  void* out;            /* bf16 (or fp32 if out_is_f32) [pixels, ldo] */
+  int ldo;
+  int out_is_f32;
+  float out_scale;
+  int epi_mode;         /* 0 linear, 1 GEGLU */
+  void* workspace;      /* split-K scratch (may be NULL => no split-K) */
+  size_t workspace_bytes;
+  int force_block_n;    /* 0 = auto; test hook */
+  int force_splits;     /* 0 = auto; test hook */
+} mdb_gemm_desc;
+
+int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream);
+/* Number of kernels mdb_gemm_conv would launch for this descriptor (1, or 2 with split-K). */
+int mdb_gemm_conv_launches(const mdb_gemm_desc* d);
+
+/* Direct (CUDA-core) convolution for tiny channel counts: conv_in 4->320 (unet_2d_condition.py:231),
+ * conv_out 320->4 (:503), BEV map encoder (magicdrive/networks/map_embedder.py:66-76).
+ * x: [n, h, w, cin] bf16 or fp32; w: fp32 [cout, kh, kw, cin]; out bf16/fp32 [n, ho, wo, cout] (+= residual). */
+int mdb_conv_direct(const void* x, int x_is_f32, int n, int h, int w, int cin, const float* wgt, const float* bias,
+                    int cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int ho, int wo,
+                    int silu, const void* residual, void* out, int out_is_f32, void* stream);
+
+/* GroupNorm (+SiLU) over NHWC, optionally over the channel-concat of two sources; writes one normalised tensor.
+ * Replaces nn.GroupNorm + SiLU (resnet.py:535,556,598,630; transformer_2d.py:145; unet_2d_condition.py:492).
+ * stats_ws: fp32 [n_img * groups * 2] scratch. */
+int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int n_img, int hw, int groups,
+                  float eps, const float* gamma, const float* beta, int silu, void* out, int ldo, float* stats_ws,
+                  void* stream);
+
+/* LayerNorm over the last dim of [rows, C] bf16 (attention.py:85,104,120; blocks.py:67-71). */
+int mdb_layernorm(const void* x, long long rows, int c, int ldx, const float* gamma, const float* beta, float eps,
+                  void* out, int ldo, void* stream);
+
+/* Fused multi-head attention forward, softmax(Q K^T * scale) V, bf16 in/out, fp32 softmax.
+ * q: [B, Lq, heads*d] with row stride ldq; k, v: [Bkv, Lk, heads*d] with row strides ldk, ldv; out like q (ldo).
+ * kv_index: device int32 [B * n_sets] or NULL.  With n_sets == 2 the kernel computes
+ *   out[b] = attn(q[b], kv[kv_index[2b]]) + attn(q[b], kv[kv_index[2b+1]])
+ * which is the cross-view "add" mode (magicdrive/networks/blocks.py:112-121, 213-217) without the 2x token
+ * duplication.  Replaces xformers efficient_attention_forward_cutlass / F.scaled_dot_product_attention
+ * (attention_processor.py:1165-1171, 1252). */
+int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
+                  int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale, void* stream);
+
+/* out = a + b (bf16), n elements (unet_2d_condition_multiview.py:464-473, 487-488). */
+int mdb_add(const void* a, const void* b, void* out, long long n, void* stream);
+
+/* Nearest-neighbour resize NHWC, src index = floor(dst * in / out) (resnet.py:156-159). */
+int mdb_upsample_nearest(const void* x, int n, int h, int w, int c, void* out, int ho, int wo, void* stream);
+
+/* Skinny linear for tiny M (time embedding MLP, time_emb_proj, camera / box encoders):
+ * out[m, n] = act(in)[m, :] . W[n, :] + b[n], W bf16 [n, k] (ldw), in/out fp32.  pre_silu applies SiLU to the input,
+ * post_silu to the output (embeddings.py:192-201; resnet.py:615-616; bbox_embedder.py:145-152). */
+int mdb_linear_small(const float* in, int m, int k, int ldi, const void* w, int ldw, const float* bias, int n,
+                     int pre_silu, int post_silu, float* out, int ldo, void* stream);
+
+/* Sinusoidal timestep embedding, flip_sin_to_cos, freq_shift (embeddings.py:24-64).  t: fp32 [m] on device. */
+int mdb_timestep_embedding(const float* t, int m, int dim, int flip_sin_to_cos, float freq_shift, float* out,
+                           void* stream);
+
+/* NeRF Fourier features [x, sin(2^k x), cos(2^k x)]_{k<num_freqs} on the last dim d of fp32 [rows, d]
+ * (magicdrive/networks/embedder.py:15-40). out fp32 [rows, d*(1+2*num_freqs)]. */
+int mdb_fourier_embed(const float* x, long long rows, int d, int num_freqs, float* out, void* stream);
+
+/* dtype conversions / layout: NCHW fp32|bf16 <-> NHWC bf16 (pipeline boundary, pipeline_bev_controlnet.py:409-411). */
+int mdb_nchw_to_nhwc(const void* x, int x_is_f32, int n, int c, int h, int w, void* out_bf16, void* stream);
+int mdb_nhwc_to_nchw(const void* x_bf16, int n, int c, int h, int w, void* out, int out_is_f32, void* stream);
+int mdb_f32_to_bf16(const float* x, void* out, long long n, void* stream);
+int mdb_bf16_to_f32(const void* x, float* out, long long n, void* stream);
+
+/* Classifier-free guidance + DDIM (eta = 0) update fused (pipeline_bev_controlnet.py:426-436;
+ * scheduling_ddim.py:325-445).  eps: fp32 [2, n] (uncond ; cond) or [1, n] if !cfg.  coef: device fp32[2] =
+ * {sqrt(abar_prev/abar_t), sqrt(1-abar_prev) - sqrt(abar_prev*(1-abar_t)/abar_t)} so x_prev = c0*x + c1*eps. */
+int mdb_cfg_ddim_step(const float* eps, int cfg, float guidance, const float* coef, float* latents, long long n,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

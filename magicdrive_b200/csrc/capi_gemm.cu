@@ -1,0 +1,250 @@
+// C-ABI launcher for the tcgen05 GEMM / implicit-GEMM convolution (include/magicdrive_b200.h: mdb_gemm_conv).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/magicdrive_b200.h"
+#include "common_host.h"
+#include "gemm_tc.cuh"
+
+using namespace mdb;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D activation map: dims (C, W, H, N) innermost first; pixel stride = ld elements.
+bool make_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int n, int h, int w, int bn, int bh, int bw,
+                  int stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool make_w_map(CUtensorMap* m, const void* ptr, int n_out, int k, int block_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)n_out};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct Plan {
+  int bn, bh, bw, tiles_n, tiles_h, tiles_w;
+  int block_n, n_tiles, splits, kb_per_split, kb_total;
+};
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// Choose the (bn, bh, bw) output-pixel box of one 128-row M tile: maximise the fraction of useful rows.
+void choose_box(int n_img, int h, int w, Plan* pl) {
+  if (h * w <= 128) {
+    int bn = 128 / (h * w);
+    if (bn > n_img) bn = n_img;
+    if (bn < 1) bn = 1;
+    pl->bn = bn, pl->bh = h, pl->bw = w;
+  } else {
+    double best = -1.0;
+    int bbh = 1, bbw = 1;
+    const int wmax = w < 128 ? w : 128;
+    for (int bw = 1; bw <= wmax; ++bw) {
+      int bh = 128 / bw;
+      if (bh > h) bh = h;
+      if (bh < 1) continue;
+      const long long tiles = (long long)((h + bh - 1) / bh) * ((w + bw - 1) / bw);
+      const double eff = (double)h * w / (double)(tiles * 128);
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > bbw)) best = eff, bbh = bh, bbw = bw;
+    }
+    pl->bn = 1, pl->bh = bbh, pl->bw = bbw;
+  }
+  pl->tiles_n = (n_img + pl->bn - 1) / pl->bn;
+  pl->tiles_h = (h + pl->bh - 1) / pl->bh;
+  pl->tiles_w = (w + pl->bw - 1) / pl->bw;
+}
+
+int validate(const mdb_gemm_desc* d) {
+  if (!d || !d->a0 || !d->w || !d->out) return set_error(MDB_ERR_INVALID, "mdb_gemm_conv: null pointer");
+  if (d->c0 <= 0 || d->c0 % 64 || d->c1 < 0 || d->c1 % 64)
+    return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: channel counts must be multiples of 64 (c0=%d c1=%d)", d->c0,
+                     d->c1);
+  if (d->c1 > 0 && !d->a1) return set_error(MDB_ERR_INVALID, "mdb_gemm_conv: c1>0 but a1 is null");
+  if (d->lda0 % 8 || (d->c1 > 0 && d->lda1 % 8) || d->ldo % 8 || (d->residual && d->ldr % 8))
+    return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: leading dimensions must be multiples of 8");
+  if (d->n_out % 8) return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: n_out must be a multiple of 8");
+  if (d->stride != 1 && d->stride != 2) return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: stride must be 1 or 2");
+  if (d->n_img <= 0 || d->h_out <= 0 || d->w_out <= 0 || d->taps_h <= 0 || d->taps_w <= 0)
+    return set_error(MDB_ERR_INVALID, "mdb_gemm_conv: bad shape");
+  if ((reinterpret_cast<uintptr_t>(d->a0) | reinterpret_cast<uintptr_t>(d->a1) | reinterpret_cast<uintptr_t>(d->w) |
+       reinterpret_cast<uintptr_t>(d->out) | reinterpret_cast<uintptr_t>(d->residual)) & 15)
+    return set_error(MDB_ERR_INVALID, "mdb_gemm_conv: pointers must be 16-byte aligned");
+  if (d->epi_mode == 1 && (d->n_out % 256 || d->residual || d->rowbias || d->out_is_f32))
+    return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: GEGLU epilogue needs n_out %% 256 == 0 and a plain bf16 output");
+  return MDB_OK;
+}
+
+void make_plan(const mdb_gemm_desc* d, Plan* pl) {
+  choose_box(d->n_img, d->h_out, d->w_out, pl);
+  const int m_tiles = pl->tiles_n * pl->tiles_h * pl->tiles_w;
+  pl->kb_total = d->taps_h * d->taps_w * ((d->c0 + d->c1) / 64);
+  const int sms = num_sms();
+  int bn_choice = 0;
+  if (d->epi_mode == 1) {
+    bn_choice = 256;
+  } else if (d->force_block_n) {
+    bn_choice = d->force_block_n;
+  } else {
+    const int cands[4] = {256, 160, 128, 64};
+    double best = 1e30;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      const int nt = (d->n_out + bn - 1) / bn;
+      const long long ctas = (long long)m_tiles * nt;
+      const long long waves = (ctas + sms - 1) / sms;
+      // cost ~ waves * (MMA time ~ bn, floored by the A-side smem/issue cost) ; prefer big tiles on ties
+      const double cost = (double)waves * (bn < 96 ? 96 : bn) * 1.0 + (double)waves * 6.0;
+      if (cost < best - 1e-9) best = cost, bn_choice = bn;
+    }
+  }
+  pl->block_n = bn_choice;
+  pl->n_tiles = (d->n_out + bn_choice - 1) / bn_choice;
+  // split-K when the grid cannot fill the machine and K is deep
+  int splits = 1;
+  const long long ctas = (long long)m_tiles * pl->n_tiles;
+  if (d->force_splits > 0) {
+    splits = d->force_splits;
+  } else if (d->epi_mode == 0 && d->workspace && ctas * 2 <= sms && pl->kb_total >= 16) {
+    splits = (int)(sms / ctas);
+    if (splits > pl->kb_total / 8) splits = pl->kb_total / 8;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > pl->kb_total) splits = pl->kb_total;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * d->n_img * d->h_out * d->w_out * d->n_out * sizeof(float);
+    if (!d->workspace || d->workspace_bytes < need || d->epi_mode != 0) splits = 1;
+  }
+  pl->kb_per_split = (pl->kb_total + splits - 1) / splits;
+  pl->splits = (pl->kb_total + pl->kb_per_split - 1) / pl->kb_per_split;  // no empty split
+}
+
+template <int BN>
+int launch(const mdb_gemm_desc* d, const Plan& pl, const CUtensorMap& tA0, const CUtensorMap& tA1,
+           const CUtensorMap& tB, const GemmParams& gp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles, pl.splits);
+  gemm_tc_kernel<BN><<<grid, 256, GemmCfg<BN>::kSmemBytes, st>>>(tA0, tA1, tB, gp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "gemm_tc_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
+  return MDB_OK;
+}
+
+}  // namespace
+
+extern "C" int mdb_gemm_conv_launches(const mdb_gemm_desc* d) {
+  if (validate(d) != MDB_OK) return MDB_ERR_INVALID;
+  Plan pl;
+  make_plan(d, &pl);
+  return pl.splits > 1 ? 2 : 1;
+}
+
+extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
+  int rc = validate(d);
+  if (rc != MDB_OK) return rc;
+  Plan pl;
+  make_plan(d, &pl);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  CUtensorMap tA0, tA1, tB;
+  if (!make_act_map(&tA0, d->a0, d->c0, d->lda0, d->n_img, d->h_in, d->w_in, pl.bn, pl.bh, pl.bw, d->stride))
+    return set_error(MDB_ERR_CUDA, "cuTensorMapEncodeTiled(A0) failed (c=%d ld=%d n=%d h=%d w=%d box=%dx%dx%d s=%d)",
+                     d->c0, d->lda0, d->n_img, d->h_in, d->w_in, pl.bn, pl.bh, pl.bw, d->stride);
+  if (d->c1 > 0) {
+    if (!make_act_map(&tA1, d->a1, d->c1, d->lda1, d->n_img, d->h_in, d->w_in, pl.bn, pl.bh, pl.bw, d->stride))
+      return set_error(MDB_ERR_CUDA, "cuTensorMapEncodeTiled(A1) failed");
+  } else {
+    tA1 = tA0;
+  }
+  const int ktot = d->taps_h * d->taps_w * (d->c0 + d->c1);
+  if (!make_w_map(&tB, d->w, d->n_out, ktot, pl.block_n))
+    return set_error(MDB_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed (n=%d k=%d)", d->n_out, ktot);
+
+  GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.n_img = d->n_img, gp.h_out = d->h_out, gp.w_out = d->w_out, gp.n_out = d->n_out;
+  gp.taps_h = d->taps_h, gp.taps_w = d->taps_w, gp.stride = d->stride, gp.pad_h = d->pad_h, gp.pad_w = d->pad_w;
+  gp.cblocks0 = d->c0 / 64, gp.cblocks1 = d->c1 / 64;
+  gp.bn = pl.bn, gp.bh = pl.bh, gp.bw = pl.bw, gp.tiles_h = pl.tiles_h, gp.tiles_w = pl.tiles_w;
+  gp.kb_per_split = pl.kb_per_split;
+  gp.epi_mode = pl.splits > 1 ? EPI_PARTIAL_F32 : d->epi_mode;
+  gp.out_is_f32 = d->out_is_f32;
+  gp.bias = d->bias, gp.rowbias = d->rowbias, gp.rowbias_ld = d->rowbias_ld;
+  gp.residual = static_cast<const __nv_bfloat16*>(d->residual), gp.ldr = d->ldr;
+  gp.out = d->out, gp.ldo = d->ldo, gp.out_scale = d->out_scale;
+  gp.partial = static_cast<float*>(d->workspace);
+
+  switch (pl.block_n) {
+    case 256: rc = launch<256>(d, pl, tA0, tA1, tB, gp, st); break;
+    case 160: rc = launch<160>(d, pl, tA0, tA1, tB, gp, st); break;
+    case 128: rc = launch<128>(d, pl, tA0, tA1, tB, gp, st); break;
+    case 64: rc = launch<64>(d, pl, tA0, tA1, tB, gp, st); break;
+    default: return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: unsupported block_n %d", pl.block_n);
+  }
+  if (rc != MDB_OK) return rc;
+  if (pl.splits > 1) {
+    const long long pixels = (long long)d->n_img * d->h_out * d->w_out;
+    const long long total4 = pixels * d->n_out / 4;
+    const int threads = 256;
+    const int blocks = (int)((total4 + threads - 1) / threads);
+    splitk_finalize_kernel<<<blocks, threads, 0, st>>>(
+        static_cast<const float*>(d->workspace), pl.splits, pixels, d->n_out, d->h_out * d->w_out, d->bias, d->rowbias,
+        d->rowbias_ld, static_cast<const __nv_bfloat16*>(d->residual), d->ldr, d->out, d->ldo, d->out_is_f32,
+        d->out_scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "splitk_finalize launch: %s", cudaGetErrorString(e));
+  }
+  return MDB_OK;
+}

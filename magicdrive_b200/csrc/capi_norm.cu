@@ -1,0 +1,231 @@
+// GroupNorm(+SiLU) over NHWC (optionally over a two-source channel concat) and LayerNorm.  HBM-bound kernels:
+// 16-byte vector loads along the contiguous channel axis, fp32 statistics, warp-shuffle / smem reductions.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/magicdrive_b200.h"
+#include "common_host.h"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x, f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2), u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+
+// ---- GroupNorm pass 1: per (image, group) sum / sum-of-squares.  blockDim = vpp * R, thread = (pixel lane r, channel vector cv)
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0,
+                                const __nv_bfloat16* __restrict__ x1, int c1, int ld1, int hw, int groups, int vpp,
+                                int R, int pix_per_cta, float* __restrict__ stats) {
+  extern __shared__ float sm[];  // [2][ctot]
+  const int ctot = c0 + c1;
+  const int img = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % vpp;
+  const int r = threadIdx.x / vpp;
+  if (r < R) {
+    const int ch = cv * 8;
+    const __nv_bfloat16* base;
+    int ld, coff;
+    if (ch < c0) base = x0, ld = ld0, coff = ch;
+    else base = x1, ld = ld1, coff = ch - c0;
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f, ss[i] = 0.f;
+    for (int p = p_begin + r; p < p_end; p += R) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(img) * hw + p) * ld + coff));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i], ss[i] += f[i] * f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sm[ch + i], s[i]);
+      atomicAdd(&sm[ctot + ch + i], ss[i]);
+    }
+  }
+  __syncthreads();
+  const int cpg = ctot / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[c], b += sm[ctot + c];
+    atomicAdd(&stats[(img * groups + g) * 2], a);
+    atomicAdd(&stats[(img * groups + g) * 2 + 1], b);
+  }
+}
+
+// ---- GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU, bf16 out.
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0,
+                                const __nv_bfloat16* __restrict__ x1, int c1, int ld1, int hw, int groups, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                const float* __restrict__ stats, __nv_bfloat16* __restrict__ out, int ldo,
+                                int pix_per_cta) {
+  extern __shared__ float sm[];  // scale[ctot], shift[ctot]
+  const int ctot = c0 + c1;
+  const int img = blockIdx.y;
+  const int cpg = ctot / groups;
+  const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  for (int c = threadIdx.x; c < ctot; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = stats[(img * groups + g) * 2] * inv_cnt;
+    float var = stats[(img * groups + g) * 2 + 1] * inv_cnt - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float a = rstd * gamma[c];
+    sm[c] = a;
+    sm[ctot + c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const int vpp = ctot / 8;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  const int total = (p_end - p_begin) * vpp;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int p = p_begin + idx / vpp;
+    const int ch = (idx % vpp) * 8;
+    const long long pix = static_cast<long long>(img) * hw + p;
+    const uint4 u = (ch < c0) ? __ldg(reinterpret_cast<const uint4*>(x0 + pix * ld0 + ch))
+                              : __ldg(reinterpret_cast<const uint4*>(x1 + pix * ld1 + (ch - c0)));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = f[i] * sm[ch + i] + sm[ctot + ch + i];
+      if (silu) y = y / (1.0f + __expf(-y));
+      f[i] = y;
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldo + ch) = pack8(f);
+  }
+}
+
+// ---- LayerNorm: one warp per row, values kept in registers (two-pass mean / variance like ATen).
+template <int MAXV>
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, int ldx,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 __nv_bfloat16* __restrict__ out, int ldo) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = c / 8;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vi * 8));
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(c);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / static_cast<float>(c) + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float y[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+      *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) = pack8(y);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int n_img, int hw,
+                             int groups, float eps, const float* gamma, const float* beta, int silu, void* out, int ldo,
+                             float* stats_ws, void* stream) {
+  using namespace mdb;
+  const int ctot = c0 + c1;
+  if (!x0 || !out || !stats_ws || !gamma || !beta) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: null pointer");
+  if (c0 % 8 || c1 % 8 || ld0 % 8 || (c1 && ld1 % 8) || ldo % 8 || ctot % groups || ctot > 4096)
+    return set_error(MDB_ERR_UNSUPPORTED, "mdb_groupnorm: unsupported channel layout (c0=%d c1=%d groups=%d)", c0, c1,
+                     groups);
+  if (c1 > 0 && !x1) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: c1>0 but x1 null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * n_img * groups, st);
+  if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "mdb_groupnorm memset: %s", cudaGetErrorString(e));
+  const int vpp = ctot / 8;
+  int R = 512 / vpp;
+  if (R < 1) R = 1;
+  if (R > 16) R = 16;
+  const int threads = vpp * R;  // <= 512
+  // enough CTAs to fill the machine: ~4 per SM over all images
+  int chunks = (148 * 4 + n_img - 1) / n_img;
+  int pix_per_cta = (hw + chunks - 1) / chunks;
+  if (pix_per_cta < R) pix_per_cta = R;
+  chunks = (hw + pix_per_cta - 1) / pix_per_cta;
+  const size_t smem = sizeof(float) * 2 * ctot;
+  gn_stats_kernel<<<dim3(chunks, n_img), threads, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, vpp,
+      R, pix_per_cta, stats_ws);
+  MDB_CHECK_LAUNCH("gn_stats_kernel");
+  gn_apply_kernel<<<dim3(chunks, n_img), 256, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
+      gamma, beta, silu, stats_ws, static_cast<__nv_bfloat16*>(out), ldo, pix_per_cta);
+  MDB_CHECK_LAUNCH("gn_apply_kernel");
+  return MDB_OK;
+}
+
+extern "C" int mdb_layernorm(const void* x, long long rows, int c, int ldx, const float* gamma, const float* beta,
+                             float eps, void* out, int ldo, void* stream) {
+  using namespace mdb;
+  if (!x || !out || !gamma || !beta) return set_error(MDB_ERR_INVALID, "mdb_layernorm: null pointer");
+  if (c % 8 || ldx % 8 || ldo % 8 || c > 8 * 32 * 8)
+    return set_error(MDB_ERR_UNSUPPORTED, "mdb_layernorm: c must be a multiple of 8 and <= 2048 (c=%d)", c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  const unsigned blocks = static_cast<unsigned>((rows + warps - 1) / warps);
+  const int nvec = c / 8;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+  if (nvec <= 64)
+    layernorm_kernel<2><<<blocks, warps * 32, 0, st>>>(xp, rows, c, ldx, gamma, beta, eps, op, ldo);
+  else if (nvec <= 160)
+    layernorm_kernel<5><<<blocks, warps * 32, 0, st>>>(xp, rows, c, ldx, gamma, beta, eps, op, ldo);
+  else
+    layernorm_kernel<8><<<blocks, warps * 32, 0, st>>>(xp, rows, c, ldx, gamma, beta, eps, op, ldo);
+  MDB_CHECK_LAUNCH("layernorm_kernel");
+  return MDB_OK;
+}

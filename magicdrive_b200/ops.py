@@ -1,0 +1,254 @@
+"""torch.Tensor-facing wrappers of the C-ABI operators.
+
+torch is plumbing only: it owns device memory and the CUDA stream; every function here forwards raw pointers to
+`libmagicdrive_b200.so` and raises if the library / a CUDA device is unavailable (no CPU or eager fallback).
+Feature maps are NHWC bf16 ("channels innermost") everywhere; a token matrix [tokens, C] is the same layout.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MdbError("magicdrive_b200 operators need CUDA tensors; there is no CPU fallback")
+
+
+_ws = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Per-device scratch (split-K partials); grown on demand outside CUDA-graph capture."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.MdbError("workspace must be sized before CUDA-graph capture (run one eager step first)")
+        buf = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in: int, c0: int, lda0: int,
+              n_out: int, taps: int = 1, stride: int = 1, pad: int = 0, h_out: Optional[int] = None,
+              w_out: Optional[int] = None, a1: Optional[torch.Tensor] = None, c1: int = 0, lda1: int = 0,
+              bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, ldr: int = 0, out: Optional[torch.Tensor] = None,
+              ldo: Optional[int] = None, out_f32: bool = False, out_scale: float = 1.0, geglu: bool = False,
+              force_block_n: int = 0, force_splits: int = 0, allow_split_k: bool = True) -> torch.Tensor:
+    """tcgen05 GEMM / implicit-GEMM conv (mdb_gemm_conv).  `a0` (and `a1`) are NHWC bf16 buffers whose pixel
+    stride is lda* elements; `w` is bf16 [n_out, taps*taps*(c0+c1)]."""
+    global _launches
+    _need_cuda(a0, w)
+    if h_out is None:
+        h_out = (h_in + 2 * pad - taps) // stride + 1
+    if w_out is None:
+        w_out = (w_in + 2 * pad - taps) // stride + 1
+    pixels = n_img * h_out * w_out
+    width = n_out // 2 if geglu else n_out
+    if out is None:
+        out = torch.empty((pixels, width), dtype=F32 if out_f32 else BF16, device=a0.device)
+        ldo = width
+    elif ldo is None:
+        ldo = out.stride(0) if out.dim() == 2 else out.shape[-1]
+    d = GemmDesc()
+    d.a0, d.a1 = _ptr(a0), _ptr(a1)
+    d.c0, d.lda0, d.c1, d.lda1 = c0, lda0, c1, lda1
+    d.n_img, d.h_in, d.w_in = n_img, h_in, w_in
+    d.w, d.n_out = _ptr(w), n_out
+    d.taps_h = d.taps_w = taps
+    d.stride, d.pad_h, d.pad_w = stride, pad, pad
+    d.h_out, d.w_out = h_out, w_out
+    d.bias = _ptr(bias)
+    d.rowbias = _ptr(rowbias)
+    d.rowbias_ld = rowbias.stride(0) if rowbias is not None else 0
+    d.residual, d.ldr = _ptr(residual), ldr
+    d.out, d.ldo, d.out_is_f32, d.out_scale = _ptr(out), ldo, int(out_f32), float(out_scale)
+    d.epi_mode = 1 if geglu else 0
+    if allow_split_k and not geglu:
+        ws = workspace(64 << 20, a0.device)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    else:
+        d.workspace, d.workspace_bytes = None, 0
+    d.force_block_n, d.force_splits = force_block_n, force_splits
+    L = _lib.lib()
+    check(L.mdb_gemm_conv(C.byref(d), _stream()), "mdb_gemm_conv")
+    _launches += L.mdb_gemm_conv_launches(C.byref(d))
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, ldo=None, geglu=False,
+           out_f32=False, out_scale=1.0, **kw) -> torch.Tensor:
+    """Token GEMM: x [M, K] bf16 (row stride may exceed K), w [N, K] bf16."""
+    m, k = x.shape
+    return gemm_conv(x, w, n_img=1, h_in=1, w_in=m, c0=k, lda0=x.stride(0), n_out=w.shape[0], bias=bias,
+                     residual=residual, ldr=(residual.stride(0) if residual is not None else 0), out=out, ldo=ldo,
+                     geglu=geglu, out_f32=out_f32, out_scale=out_scale, **kw)
+
+
+def conv_direct(x, wgt, bias, *, n, h, w, cin, cout, k, stride=(1, 1), pad=(1, 1), silu=False, residual=None,
+                out_f32=False):
+    global _launches
+    _need_cuda(x, wgt)
+    ho = (h + 2 * pad[0] - k) // stride[0] + 1
+    wo = (w + 2 * pad[1] - k) // stride[1] + 1
+    out = torch.empty((n, ho, wo, cout), dtype=F32 if out_f32 else BF16, device=x.device)
+    check(_lib.lib().mdb_conv_direct(_ptr(x), int(x.dtype == F32), n, h, w, cin, _ptr(wgt), _ptr(bias), cout, k, k,
+                                     stride[0], stride[1], pad[0], pad[1], ho, wo, int(silu), _ptr(residual),
+                                     _ptr(out), int(out_f32), _stream()), "mdb_conv_direct")
+    _launches += 1
+    return out
+
+
+_gn_ws = {}
+
+
+def groupnorm(x0, c0, ld0, n_img, hw, gamma, beta, eps, silu, x1=None, c1=0, ld1=0, groups=32):
+    global _launches
+    _need_cuda(x0)
+    out = torch.empty((n_img * hw, c0 + c1), dtype=BF16, device=x0.device)
+    stats = torch.empty((n_img * groups * 2,), dtype=F32, device=x0.device)
+    check(_lib.lib().mdb_groupnorm(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n_img, hw, groups, float(eps), _ptr(gamma),
+                                   _ptr(beta), int(silu), _ptr(out), c0 + c1, _ptr(stats), _stream()), "mdb_groupnorm")
+    _launches += 3  # memset node + stats + apply
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    global _launches
+    _need_cuda(x)
+    rows, c = x.shape
+    out = torch.empty((rows, c), dtype=BF16, device=x.device)
+    check(_lib.lib().mdb_layernorm(_ptr(x), rows, c, x.stride(0), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), c,
+                                   _stream()), "mdb_layernorm")
+    _launches += 1
+    return out
+
+
+def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=None, n_sets=1, out=None):
+    """q: [b*lq, >=heads*d] view with row stride ldq, k/v likewise; returns [b*lq, heads*d] bf16."""
+    global _launches
+    _need_cuda(q, k, v)
+    if out is None:
+        out = torch.empty((b * lq, heads * d), dtype=BF16, device=q.device)
+    check(_lib.lib().mdb_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), out.stride(0), b, heads, lq, lk,
+                                   d, _ptr(kv_index), n_sets, float(scale), _stream()), "mdb_attention")
+    _launches += 1
+    return out
+
+
+def add(a, b):
+    global _launches
+    _need_cuda(a, b)
+    out = torch.empty_like(a)
+    check(_lib.lib().mdb_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "mdb_add")
+    _launches += 1
+    return out
+
+
+def upsample_nearest(x, n, h, w, c, ho, wo):
+    global _launches
+    _need_cuda(x)
+    out = torch.empty((n * ho * wo, c), dtype=BF16, device=x.device)
+    check(_lib.lib().mdb_upsample_nearest(_ptr(x), n, h, w, c, _ptr(out), ho, wo, _stream()), "mdb_upsample_nearest")
+    _launches += 1
+    return out
+
+
+def linear_small(x, w, bias=None, pre_silu=False, post_silu=False):
+    """x fp32 [m, k]; w bf16 [n, k]; returns fp32 [m, n]."""
+    global _launches
+    _need_cuda(x, w)
+    m, k = x.shape
+    n = w.shape[0]
+    out = torch.empty((m, n), dtype=F32, device=x.device)
+    check(_lib.lib().mdb_linear_small(_ptr(x), m, k, x.stride(0), _ptr(w), w.stride(0), _ptr(bias), n, int(pre_silu),
+                                      int(post_silu), _ptr(out), n, _stream()), "mdb_linear_small")
+    _launches += 1
+    return out
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
+    global _launches
+    _need_cuda(t)
+    out = torch.empty((t.numel(), dim), dtype=F32, device=t.device)
+    check(_lib.lib().mdb_timestep_embedding(_ptr(t), t.numel(), dim, int(flip_sin_to_cos), float(freq_shift), _ptr(out),
+                                            _stream()), "mdb_timestep_embedding")
+    _launches += 1
+    return out
+
+
+def fourier_embed(x, num_freqs):
+    global _launches
+    _need_cuda(x)
+    rows, d = x.shape
+    out = torch.empty((rows, d * (1 + 2 * num_freqs)), dtype=F32, device=x.device)
+    check(_lib.lib().mdb_fourier_embed(_ptr(x), rows, d, num_freqs, _ptr(out), _stream()), "mdb_fourier_embed")
+    _launches += 1
+    return out
+
+
+def nchw_to_nhwc(x):
+    global _launches
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    if x.dtype not in (F32, BF16):
+        x = x.float()
+    out = torch.empty((n * h * w, c), dtype=BF16, device=x.device)
+    check(_lib.lib().mdb_nchw_to_nhwc(_ptr(x), int(x.dtype == F32), n, c, h, w, _ptr(out), _stream()), "mdb_nchw_to_nhwc")
+    _launches += 1
+    return out
+
+
+def nhwc_to_nchw(x, n, c, h, w, dtype=F32):
+    global _launches
+    _need_cuda(x)
+    out = torch.empty((n, c, h, w), dtype=dtype, device=x.device)
+    check(_lib.lib().mdb_nhwc_to_nchw(_ptr(x), n, c, h, w, _ptr(out), int(dtype == F32), _stream()), "mdb_nhwc_to_nchw")
+    _launches += 1
+    return out
+
+
+def f32_to_bf16(x):
+    global _launches
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.lib().mdb_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "mdb_f32_to_bf16")
+    _launches += 1
+    return out
+
+
+def cfg_ddim_step(eps, latents, coef, cfg: bool, guidance: float):
+    global _launches
+    _need_cuda(eps, latents, coef)
+    check(_lib.lib().mdb_cfg_ddim_step(_ptr(eps), int(cfg), float(guidance), _ptr(coef), _ptr(latents),
+                                       latents.numel(), _stream()), "mdb_cfg_ddim_step")
+    _launches += 1
+    return latents
