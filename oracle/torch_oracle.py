@@ -1,0 +1,357 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement (plain torch, fp32 by default) of the reference's multi-view
+denoising path.  It is the checker for the CUDA path, never the thing shipped or measured: only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it.
+
+Parity status: PINNED.  (a) the diffusers known-answer slices the reference's own tests hold for ResnetBlock2D /
+Transformer2DModel / timestep embedding / Upsample2D / Downsample2D / DDIM (tests/test_oracle_cpu.py, numbers cited
+from third_party/diffusers/tests/...) and (b) fixtures produced by running the reference itself in the build
+container through oracle/ref_shim.py (oracle/make_golden.py -> tests/golden/*.pt).
+
+Every function takes the reference's state-dict tensors by their checkpoint names and cites the reference code
+it restates (paths relative to /root/reference).  Activations are NCHW like the reference.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from magicdrive_b200 import arch
+
+SD = Dict[str, torch.Tensor]
+
+
+def _lin(sd: SD, p: str, x):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+
+
+def _conv(sd: SD, p: str, x, stride=1, padding=1):
+    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+
+
+# ---------------------------------------------------------------------------------------------- embeddings
+def timestep_embedding(timesteps, dim, flip_sin_to_cos=True, freq_shift=0.0, max_period=10000):
+    """get_timestep_embedding, third_party/diffusers/src/diffusers/models/embeddings.py:24-64."""
+    half = dim // 2
+    exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device)
+    exponent = exponent / (half - freq_shift)
+    emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+    if dim % 2 == 1:
+        emb = F.pad(emb, (0, 1, 0, 0))
+    return emb
+
+
+def time_embedding(sd: SD, t_emb):
+    """TimestepEmbedding.forward, embeddings.py:186-201 (linear_1 -> SiLU -> linear_2)."""
+    return _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", t_emb)))
+
+
+def fourier_embed(x, num_freqs):
+    """Embedder.__call__, magicdrive/networks/embedder.py:15-40 (include_input, log_sampling, [sin, cos])."""
+    out = [x]
+    for k in range(num_freqs):
+        freq = 2.0 ** k
+        out += [torch.sin(x * freq), torch.cos(x * freq)]
+    return torch.cat(out, -1)
+
+
+# ---------------------------------------------------------------------------------------------- blocks
+def resnet_block(sd: SD, p: str, x, temb, groups=32, eps=1e-5):
+    """ResnetBlock2D.forward, diffusers/models/resnet.py:590-640 (time_embedding_norm='default', scale 1)."""
+    h = F.silu(F.group_norm(x, groups, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps))
+    h = _conv(sd, p + ".conv1", h)
+    h = h + _lin(sd, p + ".time_emb_proj", F.silu(temb))[:, :, None, None]
+    h = F.silu(F.group_norm(h, groups, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], eps))
+    h = _conv(sd, p + ".conv2", h)
+    if (p + ".conv_shortcut.weight") in sd:
+        x = _conv(sd, p + ".conv_shortcut", x, padding=0)
+    return x + h
+
+
+def attention(sd: SD, p: str, x, ctx, heads):
+    """Attention + AttnProcessor2_0.__call__, diffusers/models/attention_processor.py:1202-1272."""
+    q = _lin(sd, p + ".to_q", x)
+    ctx = x if ctx is None else ctx
+    k = _lin(sd, p + ".to_k", ctx)
+    v = _lin(sd, p + ".to_v", ctx)
+    b, lq, c = q.shape
+    d = c // heads
+    qh = q.view(b, lq, heads, d).transpose(1, 2)
+    kh = k.view(b, -1, heads, d).transpose(1, 2)
+    vh = v.view(b, -1, heads, d).transpose(1, 2)
+    s = torch.softmax((qh @ kh.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+    o = (s @ vh).transpose(1, 2).reshape(b, lq, c)
+    return _lin(sd, p + ".to_out.0", o)
+
+
+def feed_forward(sd: SD, p: str, x):
+    """FeedForward with GEGLU, diffusers/models/attention.py:229-232, 276-280."""
+    h, gate = _lin(sd, p + ".net.0.proj", x).chunk(2, dim=-1)
+    return _lin(sd, p + ".net.2", h * F.gelu(gate))
+
+
+def _ln(sd, p, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+
+def transformer_block(sd: SD, p: str, x, ctx, heads, multiview: bool, neighbors=None):
+    """BasicTransformerBlock.forward (attention.py:123-182) / BasicMultiviewTransformerBlock.forward
+    (magicdrive/networks/blocks.py:144-238, 'add' mode of _construct_attn_input :112-121)."""
+    x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x), None, heads)
+    x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), ctx, heads)
+    if multiview:
+        n_cam = len(neighbors)
+        h = _ln(sd, p + ".norm4", x)
+        h = h.view(-1, n_cam, *h.shape[1:])  # (b, n, L, C)
+        B = h.shape[0]
+        q_in, kv_in, cam_order = [], [], []
+        for key, values in neighbors.items():
+            for value in values:
+                q_in.append(h[:, key])
+                kv_in.append(h[:, value])
+                cam_order += [key] * B
+        q_in, kv_in = torch.cat(q_in, 0), torch.cat(kv_in, 0)
+        cam_order = torch.tensor(cam_order)
+        raw = attention(sd, p + ".attn4", q_in, kv_in, heads)
+        out = torch.zeros_like(h)
+        for cam_i in range(n_cam):
+            sel = raw[cam_order == cam_i]  # (n_pairs*B, L, C), pair-major
+            out[:, cam_i] = sel.view(-1, B, *sel.shape[1:]).sum(0)
+        out = out.view(-1, *out.shape[2:])
+        x = x + _lin(sd, p + ".connector", out)
+    x = x + feed_forward(sd, p + ".ff", _ln(sd, p + ".norm3", x))
+    return x
+
+
+def transformer_2d(sd: SD, p: str, x, ctx, heads, multiview, neighbors=None, groups=32):
+    """Transformer2DModel.forward, diffusers/models/transformer_2d.py:276-315 (conv projections, GN eps 1e-6)."""
+    b, c, hh, ww = x.shape
+    res = x
+    h = F.group_norm(x, groups, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
+    h = _conv(sd, p + ".proj_in", h, padding=0)
+    h = h.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
+    h = transformer_block(sd, p + ".transformer_blocks.0", h, ctx, heads, multiview, neighbors)
+    h = h.reshape(b, hh, ww, c).permute(0, 3, 1, 2).contiguous()
+    return _conv(sd, p + ".proj_out", h, padding=0) + res
+
+
+def upsample(sd: SD, p: str, x, size):
+    """Upsample2D.forward with explicit output_size, resnet.py:137-172."""
+    x = F.interpolate(x, size=size, mode="nearest")
+    return _conv(sd, p, x)
+
+
+# ---------------------------------------------------------------------------------------------- networks
+def _encoder(sd, cfg, sample, emb, ctx, multiview, neighbors):
+    g, eps = cfg.norm_num_groups, cfg.norm_eps
+    skips = [sample]
+    for blk in arch.down_blocks(cfg, multiview):
+        for rs, tr in blk.layers:
+            sample = resnet_block(sd, rs.prefix, sample, emb, g, eps)
+            if tr is not None:
+                sample = transformer_2d(sd, tr.prefix, sample, ctx, tr.heads, multiview, neighbors, g)
+            skips.append(sample)
+        if blk.sampler is not None:
+            sample = _conv(sd, blk.sampler.prefix, sample, stride=2, padding=1)
+            skips.append(sample)
+    r0, tr, r1 = arch.mid_block(cfg, multiview)
+    sample = resnet_block(sd, r0.prefix, sample, emb, g, eps)
+    sample = transformer_2d(sd, tr.prefix, sample, ctx, tr.heads, multiview, neighbors, g)
+    sample = resnet_block(sd, r1.prefix, sample, emb, g, eps)
+    return sample, skips
+
+
+def unet_forward(sd: SD, cfg: arch.UNetConfig, sample, timestep, encoder_hidden_states,
+                 down_block_additional_residuals=None, mid_block_additional_residual=None):
+    """UNet2DConditionModelMultiview.forward, magicdrive/networks/unet_2d_condition_multiview.py:327-527."""
+    t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
+    t = t.reshape(-1).to(sample.device).expand(sample.shape[0]) if t.numel() == 1 else t.to(sample.device)
+    t_emb = timestep_embedding(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift).to(sample.dtype)
+    emb = time_embedding(sd, t_emb)
+    nb = cfg.neighboring_view_pair
+    sample = _conv(sd, "conv_in", sample)
+    sample, skips = _encoder(sd, cfg, sample, emb, encoder_hidden_states, True, nb)
+    if down_block_additional_residuals is not None:
+        skips = [s + r for s, r in zip(skips, down_block_additional_residuals)]
+    if mid_block_additional_residual is not None:
+        sample = sample + mid_block_additional_residual
+    g, eps = cfg.norm_num_groups, cfg.norm_eps
+    for blk in arch.up_blocks(cfg):
+        n_res = len(blk.layers)
+        res, skips = skips[-n_res:], skips[:-n_res]
+        for rs, tr in blk.layers:
+            sample = torch.cat([sample, res.pop()], dim=1)
+            sample = resnet_block(sd, rs.prefix, sample, emb, g, eps)
+            if tr is not None:
+                sample = transformer_2d(sd, tr.prefix, sample, encoder_hidden_states, tr.heads, True, nb, g)
+        if blk.sampler is not None:
+            sample = upsample(sd, blk.sampler.prefix, sample, skips[-1].shape[2:])
+    sample = F.silu(F.group_norm(sample, g, sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], eps))
+    return _conv(sd, "conv_out", sample)
+
+
+def embed_camera(camera_param, num_freqs):
+    """BEVControlNetModel._embed_camera, magicdrive/networks/unet_addon_rawbox.py:288-305: (b,n,3,7) -> (b,n,189)."""
+    b, n, c3, e = camera_param.shape
+    x = camera_param.permute(0, 1, 3, 2).reshape(b * n * e, c3)  # 'b n d c -> (b n c) d'
+    emb = fourier_embed(x, num_freqs)
+    return emb.reshape(b, n, e * emb.shape[-1])
+
+
+def bbox_embed(sd: SD, cfg: arch.ControlNetConfig, bboxes, classes, masks):
+    """ContinuousBBoxWithTextEmbedding.forward, magicdrive/networks/bbox_embedder.py:154-189 (all-xyz, no minmax)."""
+    p = "bbox_embedder"
+    B, N = classes.shape
+    bb = bboxes.reshape(B * N, *bboxes.shape[2:])
+    m = masks.flatten().unsqueeze(-1).to(sd[p + ".null_pos_feature"].dtype)
+    pos = fourier_embed(bb, cfg.bbox_num_freqs).reshape(B * N, -1).to(m.dtype)
+    pos = pos * m + sd[p + ".null_pos_feature"][None] * (1 - m)
+    cls = sd[p + "._class_tokens"][classes.flatten()]
+    cls = cls * m + sd[p + ".null_class_feature"][None] * (1 - m)
+    emb = F.silu(_lin(sd, p + ".bbox_proj", pos))
+    emb = torch.cat([emb, cls], -1)
+    emb = _lin(sd, p + ".second_linear.0", emb)
+    emb = _lin(sd, p + ".second_linear.2", F.silu(emb))
+    emb = _lin(sd, p + ".second_linear.4", F.silu(emb))
+    return emb.reshape(B, N, -1)
+
+
+def map_encode(sd: SD, cfg: arch.ControlNetConfig, cond):
+    """BEVControlNetConditioningEmbedding.forward, magicdrive/networks/map_embedder.py:66-76."""
+    layers = arch.map_encoder_layers(cfg)
+    x = cond
+    for name, _, _, stride, pad in layers[:-1]:
+        x = F.silu(F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride=stride, padding=pad))
+    name = layers[-1][0]
+    return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], padding=1)
+
+
+def controlnet_context(sd: SD, cfg: arch.ControlNetConfig, camera_param, bboxes_3d_data, encoder_hidden_states):
+    """Steps 0 / 0.5 of BEVControlNetModel.forward (unet_addon_rawbox.py:743-793) + add_cam_states (:317-336).
+    Returns (b, n_cam, 1 + len + n_box, 768)."""
+    n_cam = camera_param.shape[1]
+    cam = _lin(sd, "cam2token", embed_camera(camera_param, cfg.cam_num_freqs))  # (b, n, 768)
+    ctx = torch.cat([cam.unsqueeze(2), encoder_hidden_states.unsqueeze(1).expand(-1, n_cam, -1, -1)], dim=2)
+    if bboxes_3d_data is not None:
+        bx = bboxes_3d_data["bboxes"]
+        b_box, n_box = bx.shape[:2]
+        emb = bbox_embed(sd, cfg, bx.reshape(b_box * n_box, *bx.shape[2:]),
+                         bboxes_3d_data["classes"].reshape(b_box * n_box, -1),
+                         bboxes_3d_data["masks"].reshape(b_box * n_box, -1))
+        if n_box != n_cam:
+            emb = emb.unsqueeze(1).expand(-1, n_cam, -1, -1)
+        else:
+            emb = emb.reshape(b_box, n_cam, *emb.shape[1:])
+        ctx = torch.cat([ctx, emb], dim=2)
+    return ctx
+
+
+def uncond_cam_param(sd: SD, cfg: arch.ControlNetConfig, batch, n_cam):
+    """BEVControlNetModel.uncond_cam_param, unet_addon_rawbox.py:307-315."""
+    w = sd["uncond_cam.weight"][0]
+    return w.reshape(1, 1, -1, cfg.uncond_cam_in_dim[1]).expand(batch, n_cam, -1, -1)
+
+
+def controlnet_forward(sd: SD, cfg: arch.ControlNetConfig, sample, timestep, camera_param, bboxes_3d_data,
+                       encoder_hidden_states, controlnet_cond, conditioning_scale=1.0):
+    """BEVControlNetModel.forward (inference path), magicdrive/networks/unet_addon_rawbox.py:707-932.
+    sample (b, n, 4, h, w).  Returns (down residuals [list], mid residual, ctx (b*n, L, 768))."""
+    b, n_cam = sample.shape[:2]
+    ctx = controlnet_context(sd, cfg, camera_param, bboxes_3d_data, encoder_hidden_states)
+    t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
+    t = t.reshape(-1).to(sample.device)
+    t_emb = timestep_embedding(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift).to(sample.dtype)
+    emb = time_embedding(sd, t_emb)
+    x = sample.reshape(b * n_cam, *sample.shape[2:])
+    ctx = ctx.reshape(b * n_cam, *ctx.shape[2:])
+    if emb.shape[0] < x.shape[0]:
+        emb = emb.repeat_interleave(n_cam, dim=0)  # 'b ... -> (b repeat) ...'
+    cond = controlnet_cond.repeat_interleave(n_cam, dim=0)
+    x = _conv(sd, "conv_in", x) + map_encode(sd, cfg, cond)
+    x, skips = _encoder(sd, cfg, x, emb, ctx, False, None)
+    down = [F.conv2d(s, sd[f"controlnet_down_blocks.{i}.weight"], sd[f"controlnet_down_blocks.{i}.bias"]) * conditioning_scale
+            for i, s in enumerate(skips)]
+    mid = F.conv2d(x, sd["controlnet_mid_block.weight"], sd["controlnet_mid_block.bias"]) * conditioning_scale
+    return down, mid, ctx
+
+
+# ---------------------------------------------------------------------------------------------- scheduler + loop
+class DDIM:
+    """DDIMScheduler (scaled_linear betas, clip_sample False, set_alpha_to_one False, steps_offset 1, eta 0):
+    third_party/diffusers/src/diffusers/schedulers/scheduling_ddim.py:120-160 (init), 287-323 (set_timesteps,
+    'leading' spacing), 325-445 (step)."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, steps_offset=1):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.T = num_train_timesteps
+        self.steps_offset = steps_offset
+
+    def set_timesteps(self, n):
+        import numpy as np
+        self.n = n
+        ratio = self.T // n
+        ts = (np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64) + self.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+        return self.timesteps
+
+    def coefficients(self, t: int):
+        """x_prev = c0 * x + c1 * eps (algebraically identical to step() with eta = 0)."""
+        prev = t - self.T // self.n
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        c0 = (a_p / a_t) ** 0.5
+        c1 = (1 - a_p) ** 0.5 - (a_p * (1 - a_t) / a_t) ** 0.5
+        return float(c0), float(c1)
+
+    def step(self, eps, t: int, x):
+        prev = t - self.T // self.n
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        x0 = (x - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+        return a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
+
+
+def add_uncond_to_kwargs(sd: SD, ccfg, camera_param, bboxes_3d_data):
+    """BEVControlNetModel.add_uncond_to_kwargs (unet_addon_rawbox.py:625-682), max_len=None: uncond first."""
+    b, n_cam = camera_param.shape[:2]
+    cam = torch.cat([uncond_cam_param(sd, ccfg, b, n_cam).to(camera_param), camera_param])
+    boxes = None
+    if bboxes_3d_data is not None:
+        boxes = {k: torch.cat([torch.zeros_like(v), v]) for k, v in bboxes_3d_data.items()}
+    return cam, boxes
+
+
+def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_prompt_embeds, camera_param,
+                 bboxes_3d_data, bev_map, num_inference_steps, guidance_scale, return_all=False):
+    """StableDiffusionBEVControlNetPipeline.__call__ steps 5-8 (magicdrive/pipeline/pipeline_bev_controlnet.py:
+    303-451) with DDIM eta=0 and output_type='latent'.  latents: (b, 4, h, w) initial noise (shared by the views,
+    :326).  Returns (b, n_cam, 4, h, w)."""
+    sched = DDIM()
+    timesteps = sched.set_timesteps(num_inference_steps)
+    n_cam = camera_param.shape[1]
+    cfg_on = guidance_scale > 1.0
+    lat = torch.stack([latents] * n_cam, dim=1)
+    text = torch.cat([negative_prompt_embeds, prompt_embeds]) if cfg_on else prompt_embeds
+    image = torch.cat([bev_map, bev_map]) if cfg_on else bev_map
+    cam, boxes = (add_uncond_to_kwargs(csd, ccfg, camera_param, bboxes_3d_data) if cfg_on
+                  else (camera_param, bboxes_3d_data))
+    hist = []
+    for t in timesteps.tolist():
+        inp = torch.cat([lat] * 2) if cfg_on else lat
+        tt = torch.full((inp.shape[0],), t, dtype=torch.int64)
+        down, mid, ctx = controlnet_forward(csd, ccfg, inp, tt, cam, boxes, text, image)
+        x = inp.reshape(-1, *inp.shape[2:])
+        eps = unet_forward(usd, ucfg, x, torch.tensor(t), ctx, down, mid)
+        if cfg_on:
+            eu, ec = eps.chunk(2)
+            eps = eu + guidance_scale * (ec - eu)
+        flat = lat.reshape(-1, *lat.shape[2:])
+        lat = sched.step(eps, t, flat).reshape(lat.shape)
+        if return_all:
+            hist.append(lat.clone())
+    return (lat, hist) if return_all else lat
