@@ -330,5 +330,5 @@ def synthetic_state_dict(shapes, seed: int = 0, scale: float = 1.0):
             a = rng.standard_normal(shape, dtype=np.float32)
         else:  # biases, null features
             a = 0.05 * rng.standard_normal(shape, dtype=np.float32)
-        sd[name] = torch.from_numpy(np.ascontiguousarray(a))
+        sd[name] = torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
     return sd

@@ -1,0 +1,406 @@
+"""CUDA execution of the two hot-path networks over the C-ABI operators (magicdrive_b200.ops).
+
+Dataflow differs from the reference on purpose (B200-first), results do not:
+  * activations are bf16 NHWC == [tokens, C]: the NCHW<->token permutes of Transformer2DModel
+    (transformer_2d.py:286,305) and the 1x1-conv / Linear distinction vanish;
+  * skip-connection concats (unet_2d_blocks.py:1984,2086) are never materialised: GroupNorm and the convolutions
+    read two sources;
+  * self / cross-view attention use one fused QKV GEMM; cross-view attention reads the neighbours' K/V in place
+    (kv_index) instead of duplicating every view's tokens twice (blocks.py:113-121) and `connector(to_out(.))`
+    is folded into one GEMM: Wc(Wo(o_l + o_r) + 2 b_o) + b_c  (blocks.py:203-222);
+  * everything that does not depend on the latents is hoisted out of the step: text-context K/V projections,
+    camera / box tokens, the BEV-map encoder (computed once per scene, not per view per step), and all 22+10
+    `time_emb_proj` linears run as one skinny GEMM.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import arch, ops
+from .params import pack_conv_weight, pack_geglu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class FMap:
+    """A feature map: data is [n*h*w, c] bf16 (NHWC)."""
+    data: torch.Tensor
+    n: int
+    h: int
+    w: int
+    c: int
+
+
+def _bf(t):
+    return t.detach().to(dtype=BF16).contiguous()
+
+
+def _f32(t):
+    return t.detach().to(dtype=F32).contiguous()
+
+
+class _Weights:
+    """Packs a reference state dict into kernel-ready device tensors (bf16 K-major matrices, fp32 biases)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device):
+        self.sd = sd
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def raw(self, key):
+        return self.sd[key].detach().to(self.device)
+
+    def conv(self, p):
+        if p + ".w" not in self.t:
+            self.t[p + ".w"] = pack_conv_weight(self.raw(p + ".weight").float())
+            self.t[p + ".b"] = _f32(self.raw(p + ".bias"))
+        return self.t[p + ".w"], self.t[p + ".b"]
+
+    def conv_direct(self, p):
+        if p + ".wd" not in self.t:
+            self.t[p + ".wd"] = _f32(self.raw(p + ".weight").float().permute(0, 2, 3, 1))
+            self.t[p + ".b"] = _f32(self.raw(p + ".bias"))
+        return self.t[p + ".wd"], self.t[p + ".b"]
+
+    def lin(self, p, bias=True):
+        if p + ".w" not in self.t:
+            self.t[p + ".w"] = _bf(self.raw(p + ".weight"))
+            self.t[p + ".b"] = _f32(self.raw(p + ".bias")) if bias else None
+        return self.t[p + ".w"], self.t[p + ".b"]
+
+    def norm(self, p):
+        if p + ".g" not in self.t:
+            self.t[p + ".g"] = _f32(self.raw(p + ".weight"))
+            self.t[p + ".beta"] = _f32(self.raw(p + ".bias"))
+        return self.t[p + ".g"], self.t[p + ".beta"]
+
+    def cat_lin(self, name, prefixes, suffix=".weight"):
+        if name not in self.t:
+            self.t[name] = _bf(torch.cat([self.raw(p + suffix) for p in prefixes], 0))
+        return self.t[name]
+
+    def geglu(self, p):
+        if p + ".gw" not in self.t:
+            w, b = pack_geglu(self.raw(p + ".weight").float(), self.raw(p + ".bias").float())
+            self.t[p + ".gw"], self.t[p + ".gb"] = w, b
+        return self.t[p + ".gw"], self.t[p + ".gb"]
+
+    def folded_connector(self, blk):
+        """W' = Wc @ Wo, b' = 2 Wc b_o + b_c  (fp32 fold, bf16 storage)."""
+        k = blk + ".attn4.fold"
+        if k + ".w" not in self.t:
+            wo = self.raw(blk + ".attn4.to_out.0.weight").float()
+            bo = self.raw(blk + ".attn4.to_out.0.bias").float()
+            wc = self.raw(blk + ".connector.weight").float()
+            bc = self.raw(blk + ".connector.bias").float()
+            self.t[k + ".w"] = _bf(wc @ wo)
+            self.t[k + ".b"] = _f32(2.0 * (wc @ bo) + bc)
+        return self.t[k + ".w"], self.t[k + ".b"]
+
+
+class _Net:
+    """Shared machinery of the UNet and the ControlNet encoder."""
+
+    def __init__(self, cfg, sd, device, multiview: bool):
+        self.cfg = cfg
+        self.W = _Weights(sd, device)
+        self.device = device
+        self.multiview = multiview
+        self.down = arch.down_blocks(cfg, multiview)
+        self.mid = arch.mid_block(cfg, multiview)
+        self.resnets: List[arch.ResnetSpec] = [rs for b in self.down for rs, _ in b.layers] + [self.mid[0], self.mid[2]]
+        self.transformers: List[arch.TransformerSpec] = [tr for b in self.down for _, tr in b.layers if tr] + [self.mid[1]]
+        self._kv_idx = {}
+
+    # ---------------------------------------------------------------- time embedding
+    def _finalize_specs(self):
+        self.temb_off, off = {}, 0
+        for rs in self.resnets:
+            self.temb_off[rs.prefix] = off
+            off += rs.cout
+        self.temb_total = off
+
+    def time_embed(self, t_f32: torch.Tensor) -> torch.Tensor:
+        """t [V] fp32 -> all resnets' time_emb_proj(silu(emb)) as one fp32 [V, sum(cout)] matrix
+        (embeddings.py:24-64,186-201; resnet.py:612-616)."""
+        cfg = self.cfg
+        te = ops.timestep_embedding(t_f32, cfg.block_out_channels[0], cfg.flip_sin_to_cos, float(cfg.freq_shift))
+        w1, b1 = self.W.lin("time_embedding.linear_1")
+        w2, b2 = self.W.lin("time_embedding.linear_2")
+        e = ops.linear_small(te, w1, b1, post_silu=True)
+        e = ops.linear_small(e, w2, b2)
+        wcat = self.W.cat_lin("temb.wcat", [rs.prefix + ".time_emb_proj" for rs in self.resnets])
+        if "temb.bcat" not in self.W.t:
+            self.W.t["temb.bcat"] = _f32(torch.cat([self.W.raw(rs.prefix + ".time_emb_proj.bias") for rs in self.resnets]))
+        return ops.linear_small(e, wcat, self.W.t["temb.bcat"], pre_silu=True)
+
+    # ---------------------------------------------------------------- blocks
+    def resnet(self, rs: arch.ResnetSpec, x: FMap, temb_all: torch.Tensor, skip: Optional[FMap] = None) -> FMap:
+        """ResnetBlock2D.forward (resnet.py:590-640); `skip` is the second half of the channel concat."""
+        W, cfg = self.W, self.cfg
+        c0 = x.c
+        c1 = skip.c if skip is not None else 0
+        assert c0 + c1 == rs.cin, (rs.prefix, c0, c1, rs.cin)
+        hw = x.h * x.w
+        x1 = skip.data if skip is not None else None
+        g1, be1 = W.norm(rs.prefix + ".norm1")
+        h = ops.groupnorm(x.data, c0, c0, x.n, hw, g1, be1, cfg.norm_eps, True, x1=x1, c1=c1, ld1=c1,
+                          groups=cfg.norm_num_groups)
+        w1, b1 = W.conv(rs.prefix + ".conv1")
+        off = self.temb_off[rs.prefix]
+        h = ops.gemm_conv(h, w1, n_img=x.n, h_in=x.h, w_in=x.w, c0=rs.cin, lda0=rs.cin, n_out=rs.cout, taps=3, pad=1,
+                          bias=b1, rowbias=temb_all[:, off:off + rs.cout])
+        g2, be2 = W.norm(rs.prefix + ".norm2")
+        h = ops.groupnorm(h, rs.cout, rs.cout, x.n, hw, g2, be2, cfg.norm_eps, True, groups=cfg.norm_num_groups)
+        if rs.shortcut:
+            ws, bs = W.conv(rs.prefix + ".conv_shortcut")
+            res = ops.gemm_conv(x.data, ws, n_img=x.n, h_in=x.h, w_in=x.w, c0=c0, lda0=c0, a1=x1, c1=c1, lda1=c1,
+                                n_out=rs.cout, bias=bs)
+        else:
+            assert skip is None
+            res = x.data
+        w2, b2 = W.conv(rs.prefix + ".conv2")
+        out = ops.gemm_conv(h, w2, n_img=x.n, h_in=x.h, w_in=x.w, c0=rs.cout, lda0=rs.cout, n_out=rs.cout, taps=3,
+                            pad=1, bias=b2, residual=res, ldr=rs.cout)
+        return FMap(out, x.n, x.h, x.w, rs.cout)
+
+    def kv_index(self, n_views: int) -> torch.Tensor:
+        """[V, 2] int32: the two ring neighbours of each view inside its own scene (Nuscenes.yaml:27-33)."""
+        if n_views not in self._kv_idx:
+            nb = self.cfg.neighboring_view_pair
+            n_cam = len(nb)
+            assert n_views % n_cam == 0
+            idx = [[s * n_cam + nb[i][0], s * n_cam + nb[i][1]] for s in range(n_views // n_cam) for i in range(n_cam)]
+            self._kv_idx[n_views] = torch.tensor(idx, dtype=torch.int32, device=self.device)
+        return self._kv_idx[n_views]
+
+    def context_kv(self, ctx_bf16: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """attn2 K/V projections of the conditioning tokens for every transformer (step-invariant).
+        ctx: [V*Lc, 768] bf16 -> {prefix: [V*Lc, 2C] bf16}."""
+        out = {}
+        for tr in self.transformers:
+            blk = tr.prefix + ".transformer_blocks.0"
+            wkv = self.W.cat_lin(blk + ".attn2.wkv", [blk + ".attn2.to_k", blk + ".attn2.to_v"])
+            out[tr.prefix] = ops.linear(ctx_bf16, wkv)
+        return out
+
+    def transformer(self, tr: arch.TransformerSpec, x: FMap, ctx_kv: Dict[str, torch.Tensor], lc: int) -> FMap:
+        """Transformer2DModel.forward (transformer_2d.py:276-315) around BasicTransformerBlock (attention.py:123-182)
+        or BasicMultiviewTransformerBlock (magicdrive/networks/blocks.py:144-238)."""
+        W, cfg = self.W, self.cfg
+        C, heads = tr.c, tr.heads
+        d = C // heads
+        V, L = x.n, x.h * x.w
+        M = V * L
+        scale = d ** -0.5
+        p = tr.prefix
+        blk = p + ".transformer_blocks.0"
+        g, b = W.norm(p + ".norm")
+        h = ops.groupnorm(x.data, C, C, V, L, g, b, 1e-6, False, groups=cfg.norm_num_groups)
+        wi, bi = W.conv(p + ".proj_in")
+        X = ops.linear(h, wi, bias=bi)
+        # --- self attention
+        g, b = W.norm(blk + ".norm1")
+        n1 = ops.layernorm(X, g, b)
+        wqkv = W.cat_lin(blk + ".attn1.wqkv", [blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
+        qkv = ops.linear(n1, wqkv)
+        o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C, ldk=3 * C,
+                          ldv=3 * C, scale=scale)
+        wo, bo = W.lin(blk + ".attn1.to_out.0")
+        X = ops.linear(o, wo, bias=bo, residual=X)
+        # --- conditioning cross attention (camera + text + box tokens)
+        g, b = W.norm(blk + ".norm2")
+        n2 = ops.layernorm(X, g, b)
+        wq, _ = W.lin(blk + ".attn2.to_q", bias=False)
+        q = ops.linear(n2, wq)
+        kv = ctx_kv[p]
+        o = ops.attention(q, kv, kv[:, C:], b=V, heads=heads, lq=L, lk=lc, d=d, ldq=C, ldk=2 * C, ldv=2 * C, scale=scale)
+        wo, bo = W.lin(blk + ".attn2.to_out.0")
+        X = ops.linear(o, wo, bias=bo, residual=X)
+        # --- cross-view attention
+        if tr.multiview:
+            if cfg.neighboring_attn_type != "add" or cfg.zero_module_type != "zero_linear":
+                raise NotImplementedError("only neighboring_attn_type='add' with the zero_linear connector (the shipped "
+                                          "configs/model/SDv1.5mv_rawbox.yaml:19-20) is implemented")
+            g, b = W.norm(blk + ".norm4")
+            n4 = ops.layernorm(X, g, b)
+            wqkv = W.cat_lin(blk + ".attn4.wqkv", [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
+            qkv = ops.linear(n4, wqkv)
+            o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C, ldk=3 * C,
+                              ldv=3 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
+            wf, bf_ = W.folded_connector(blk)
+            X = ops.linear(o, wf, bias=bf_, residual=X)
+        # --- GEGLU feed-forward
+        g, b = W.norm(blk + ".norm3")
+        n3 = ops.layernorm(X, g, b)
+        wg, bg = W.geglu(blk + ".ff.net.0.proj")
+        hg = ops.linear(n3, wg, bias=bg, geglu=True)
+        w2, b2 = W.lin(blk + ".ff.net.2")
+        X = ops.linear(hg, w2, bias=b2, residual=X)
+        wp, bp = W.conv(p + ".proj_out")
+        out = ops.linear(X, wp, bias=bp, residual=x.data)
+        return FMap(out, V, x.h, x.w, C)
+
+    def downsample(self, sp: arch.SamplerSpec, x: FMap) -> FMap:
+        w, b = self.W.conv(sp.prefix)
+        ho, wo = (x.h + 2 - 3) // 2 + 1, (x.w + 2 - 3) // 2 + 1
+        out = ops.gemm_conv(x.data, w, n_img=x.n, h_in=x.h, w_in=x.w, c0=x.c, lda0=x.c, n_out=sp.c, taps=3, stride=2,
+                            pad=1, bias=b)
+        return FMap(out, x.n, ho, wo, sp.c)
+
+    def encoder(self, x: FMap, temb_all, ctx_kv, lc):
+        skips = [x]
+        for blk in self.down:
+            for rs, tr in blk.layers:
+                x = self.resnet(rs, x, temb_all)
+                if tr is not None:
+                    x = self.transformer(tr, x, ctx_kv, lc)
+                skips.append(x)
+            if blk.sampler is not None:
+                x = self.downsample(blk.sampler, x)
+                skips.append(x)
+        r0, tr, r1 = self.mid
+        x = self.resnet(r0, x, temb_all)
+        x = self.transformer(tr, x, ctx_kv, lc)
+        x = self.resnet(r1, x, temb_all)
+        return x, skips
+
+    def conv_in(self, x_nhwc: torch.Tensor, n, h, w, residual=None) -> FMap:
+        wd, b = self.W.conv_direct("conv_in")
+        c0 = self.cfg.block_out_channels[0]
+        out = ops.conv_direct(x_nhwc, wd, b, n=n, h=h, w=w, cin=self.cfg.in_channels, cout=c0, k=3, residual=residual)
+        return FMap(out.view(n * h * w, c0), n, h, w, c0)
+
+
+class UNetEngine(_Net):
+    """UNet2DConditionModelMultiview.forward on the GPU (unet_2d_condition_multiview.py:327-527)."""
+
+    def __init__(self, cfg: arch.UNetConfig, sd, device):
+        super().__init__(cfg, sd, device, multiview=True)
+        self.up = arch.up_blocks(cfg)
+        self.resnets += [rs for b in self.up for rs, _ in b.layers]
+        self.transformers += [tr for b in self.up for _, tr in b.layers if tr]
+        self._finalize_specs()
+
+    def forward(self, latents_nhwc: torch.Tensor, n, h, w, t_f32, ctx_kv, lc, down_res: Optional[List[torch.Tensor]] = None,
+                mid_res: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """latents [n*h*w, 4] bf16 -> predicted noise fp32 NHWC [n, h, w, out_channels]."""
+        cfg = self.cfg
+        temb_all = self.time_embed(t_f32)
+        x = self.conv_in(latents_nhwc, n, h, w)
+        x, skips = self.encoder(x, temb_all, ctx_kv, lc)
+        if down_res is not None:
+            skips = [FMap(ops.add(s.data, r), s.n, s.h, s.w, s.c) for s, r in zip(skips, down_res)]
+        if mid_res is not None:
+            x = FMap(ops.add(x.data, mid_res), x.n, x.h, x.w, x.c)
+        for blk in self.up:
+            for rs, tr in blk.layers:
+                x = self.resnet(rs, x, temb_all, skip=skips.pop())
+                if tr is not None:
+                    x = self.transformer(tr, x, ctx_kv, lc)
+            if blk.sampler is not None:
+                tgt = skips[-1]
+                up = ops.upsample_nearest(x.data, x.n, x.h, x.w, x.c, tgt.h, tgt.w)
+                wu, bu = self.W.conv(blk.sampler.prefix)
+                out = ops.gemm_conv(up, wu, n_img=x.n, h_in=tgt.h, w_in=tgt.w, c0=x.c, lda0=x.c, n_out=x.c, taps=3, pad=1,
+                                    bias=bu)
+                x = FMap(out, x.n, tgt.h, tgt.w, x.c)
+        g, b = self.W.norm("conv_norm_out")
+        hn = ops.groupnorm(x.data, x.c, x.c, x.n, x.h * x.w, g, b, cfg.norm_eps, True, groups=cfg.norm_num_groups)
+        wd, bo = self.W.conv_direct("conv_out")
+        return ops.conv_direct(hn, wd, bo, n=x.n, h=x.h, w=x.w, cin=x.c, cout=cfg.out_channels, k=3, out_f32=True)
+
+
+class ControlNetEngine(_Net):
+    """BEVControlNetModel.forward on the GPU (magicdrive/networks/unet_addon_rawbox.py:707-932)."""
+
+    def __init__(self, cfg: arch.ControlNetConfig, sd, device):
+        super().__init__(cfg, sd, device, multiview=False)
+        self._finalize_specs()
+        self.res_channels = arch.controlnet_residual_channels(cfg)
+
+    # ---------------------------------------------------------------- step-invariant conditioning
+    def camera_tokens(self, camera_param: torch.Tensor) -> torch.Tensor:
+        """(b, n, 3, 7) -> (b*n, 768) fp32: _embed_camera + cam2token (unet_addon_rawbox.py:288-305, 329)."""
+        b, n, c3, e = camera_param.shape
+        x = camera_param.to(self.device, F32).permute(0, 1, 3, 2).reshape(b * n * e, c3).contiguous()
+        emb = ops.fourier_embed(x, self.cfg.cam_num_freqs).view(b * n, -1)
+        w, bias = self.W.lin("cam2token")
+        return ops.linear_small(emb, w, bias)
+
+    def uncond_cam_param(self, batch, n_cam):
+        w = self.W.raw("uncond_cam.weight")[0].float()
+        return w.reshape(1, 1, -1, self.cfg.uncond_cam_in_dim[1]).expand(batch, n_cam, -1, -1)
+
+    def box_tokens(self, bboxes, classes, masks) -> torch.Tensor:
+        """(B, N, 8, 3), (B, N), (B, N) -> (B*N, 768) fp32 (bbox_embedder.py:154-189)."""
+        W, cfg = self.W, self.cfg
+        p = "bbox_embedder"
+        B, N = classes.shape
+        bb = bboxes.to(self.device, F32).reshape(B * N * cfg.bbox_points, 3).contiguous()
+        m = masks.to(self.device).reshape(B * N, 1).to(F32)
+        pos = ops.fourier_embed(bb, cfg.bbox_num_freqs).view(B * N, -1)
+        # masked select between the embedding and the learned null features: O(B*N*1000) elementwise glue on the
+        # step-invariant path (once per call), kept in torch
+        pos = pos * m + W.raw(p + ".null_pos_feature").float()[None] * (1 - m)
+        cls = W.raw(p + "._class_tokens").float()[classes.to(self.device).reshape(-1)]
+        cls = cls * m + W.raw(p + ".null_class_feature").float()[None] * (1 - m)
+        w, b = W.lin(p + ".bbox_proj")
+        emb = ops.linear_small(pos.contiguous(), w, b, post_silu=True)
+        emb = torch.cat([emb, cls], -1).contiguous()
+        w, b = W.lin(p + ".second_linear.0")
+        emb = ops.linear_small(emb, w, b, post_silu=True)
+        w, b = W.lin(p + ".second_linear.2")
+        emb = ops.linear_small(emb, w, b, post_silu=True)
+        w, b = W.lin(p + ".second_linear.4")
+        return ops.linear_small(emb, w, b)
+
+    def context(self, camera_param, bboxes_3d_data, encoder_hidden_states) -> torch.Tensor:
+        """encoder_hidden_states_with_cam: (b*n_cam, 1 + len + n_box, 768) fp32 (unet_addon_rawbox.py:743-793)."""
+        b, n_cam = camera_param.shape[:2]
+        cam = self.camera_tokens(camera_param).view(b, n_cam, 1, -1)
+        text = encoder_hidden_states.to(self.device, F32)
+        parts = [cam, text.unsqueeze(1).expand(-1, n_cam, -1, -1)]
+        if bboxes_3d_data is not None:
+            bx = bboxes_3d_data["bboxes"]
+            b_box, n_box = bx.shape[:2]
+            emb = self.box_tokens(bx.reshape(b_box * n_box, *bx.shape[2:]),
+                                  bboxes_3d_data["classes"].reshape(b_box * n_box, -1),
+                                  bboxes_3d_data["masks"].reshape(b_box * n_box, -1))
+            emb = emb.view(b_box, n_box, -1, emb.shape[-1])
+            if n_box != n_cam:
+                emb = emb.expand(-1, n_cam, -1, -1)
+            parts.append(emb)
+        ctx = torch.cat(parts, dim=2)
+        return ctx.reshape(b * n_cam, ctx.shape[2], ctx.shape[3]).contiguous()
+
+    def map_embedding(self, cond: torch.Tensor) -> torch.Tensor:
+        """BEV map (b, 8, H, W) -> [b, h, w, 320] bf16 NHWC, once per scene (map_embedder.py:66-76)."""
+        x = cond.to(self.device, F32).permute(0, 2, 3, 1).contiguous()
+        n, h, w = x.shape[0], x.shape[1], x.shape[2]
+        layers = arch.map_encoder_layers(self.cfg)
+        for i, (name, ci, co, stride, pad) in enumerate(layers):
+            wd, bias = self.W.conv_direct(name)
+            last = i == len(layers) - 1
+            x = ops.conv_direct(x, wd, bias, n=n, h=h, w=w, cin=ci, cout=co, k=3, stride=stride, pad=pad, silu=not last,
+                                out_f32=not last)
+            h, w = x.shape[1], x.shape[2]
+        return x  # bf16 [b, h, w, 320]
+
+    # ---------------------------------------------------------------- per-step
+    def forward(self, latents_nhwc, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view: torch.Tensor,
+                conditioning_scale: float = 1.0):
+        """latents [n*h*w, 4] bf16 (n = scenes*views); t_f32 [n]; map_emb_per_view [n, h, w, 320] bf16.
+        Returns (12 + 1 residual maps as [pixels, C] bf16 tensors)."""
+        temb_all = self.time_embed(t_f32)
+        x = self.conv_in(latents_nhwc, n, h, w, residual=map_emb_per_view)
+        x, skips = self.encoder(x, temb_all, ctx_kv, lc)
+        down = []
+        for i, s in enumerate(skips):
+            wz, bz = self.W.conv(f"controlnet_down_blocks.{i}")
+            down.append(ops.linear(s.data, wz, bias=bz, out_scale=conditioning_scale))
+        wz, bz = self.W.conv("controlnet_mid_block")
+        mid = ops.linear(x.data, wz, bias=bz, out_scale=conditioning_scale)
+        return down, mid, skips, x

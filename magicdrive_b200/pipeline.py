@@ -1,0 +1,154 @@
+"""The denoising loop of StableDiffusionBEVControlNetPipeline.__call__ (magicdrive/pipeline/pipeline_bev_controlnet.py:
+303-451) on top of the B200 engines: classifier-free-guidance batching ([uncond ; cond]), ControlNet -> UNet ->
+guidance -> DDIM update per step, with everything step-invariant hoisted and one whole step captured in a CUDA graph.
+
+Differences from the reference that do not change results: latents stay fp32 and NHWC-resident between steps
+(the reference re-stacks / rearranges 5-D tensors every step); the DDIM update (eta = 0) is fused with the guidance
+combine; `timestep` and the two DDIM coefficients are read from device memory so the captured graph is replayed
+unchanged for every step.  The reference refuses DDIM only because `scheduler.step` accepts a `generator`
+(:93-97); eta = 0 is deterministic, so no generator is needed.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .models import BEVControlNetModel, UNet2DConditionModelMultiview
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+class DDIMSchedule:
+    """DDIMScheduler(beta 0.00085-0.012 scaled_linear, clip_sample False, set_alpha_to_one False, steps_offset 1,
+    'leading' spacing): scheduling_ddim.py:120-160, 287-323, 325-445 with eta = 0 reduced to x' = c0 x + c1 eps."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, steps_offset=1):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0).double()  # fp32 table like the reference, fp64 math after
+        self.T = num_train_timesteps
+        self.steps_offset = steps_offset
+
+    def set_timesteps(self, n: int):
+        ratio = self.T // n
+        self.timesteps = [int(round(i * ratio)) + self.steps_offset for i in range(n)][::-1]
+        coefs = []
+        for t in self.timesteps:
+            prev = t - ratio
+            a_t = self.alphas_cumprod[t]
+            a_p = self.alphas_cumprod[prev] if prev >= 0 else self.alphas_cumprod[0]
+            c0 = (a_p / a_t) ** 0.5
+            c1 = (1 - a_p) ** 0.5 - (a_p * (1 - a_t) / a_t) ** 0.5
+            coefs.append([float(c0), float(c1)])
+        self.coefs = coefs
+        return self.timesteps
+
+
+class BEVControlNetDenoiser:
+    """Call-compatible core of StableDiffusionBEVControlNetPipeline for `output_type="latent"` with precomputed
+    prompt embeddings (the CLIP text encoder and the VAE sit outside the hot path: SURVEY.md §2.1)."""
+
+    def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True):
+        self.unet, self.controlnet = unet, controlnet
+        self.scheduler = DDIMSchedule()
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._graph_key = None
+
+    # ------------------------------------------------------------------ one step on resident buffers
+    def _step(self, st):
+        ue, ce = st["ue"], st["ce"]
+        V, h, w = st["V"], st["h"], st["w"]
+        lat = st["latents"]  # fp32 [S*ncam*h*w, 4] NHWC, S scenes (no CFG duplication)
+        x = ops.f32_to_bf16(lat)
+        if st["cfg"]:
+            x = torch.cat([x, x], 0)  # [uncond ; cond] share the latents (:352-354)
+        down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"])
+        eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid)  # fp32 [V, h, w, 4]
+        ops.cfg_ddim_step(eps.view(2 if st["cfg"] else 1, -1), lat, st["coef_dev"], st["cfg"], st["guidance"])
+
+    @torch.no_grad()
+    def prepare(self, latents, prompt_embeds, negative_prompt_embeds, camera_param, bboxes_3d_data, image,
+                guidance_scale=2.0, controlnet_conditioning_scale=1.0):
+        """Host -> device staging + all step-invariant work.  latents: (S, 4, h, w) initial noise shared by the views
+        (:326) or (S, n_cam, 4, h, w)."""
+        dev = self.unet.device
+        cn, un = self.controlnet, self.unet
+        cfg = guidance_scale > 1.0
+        camera_param = camera_param.to(dev, F32)
+        S, n_cam = camera_param.shape[:2]
+        prompt_embeds = prompt_embeds.to(dev, F32)
+        image = image.to(dev, F32)
+        boxes = None if bboxes_3d_data is None else {k: v.to(dev) for k, v in bboxes_3d_data.items()}
+        if cfg:
+            negative_prompt_embeds = negative_prompt_embeds.to(dev, F32)
+            kw = cn.add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=boxes, image=image)
+            camera_param, boxes = kw["camera_param"], kw["bboxes_3d_data"]
+            text = torch.cat([negative_prompt_embeds, prompt_embeds])
+            image = torch.cat([image, image])
+        else:
+            text = prompt_embeds
+        cond = cn.prepare_conditions(camera_param, boxes, text, image)
+        u_kv, lc = un.prepare_context(cond["ctx"])
+        lat = latents.to(dev, F32)
+        if lat.dim() == 4:
+            lat = torch.stack([lat] * n_cam, dim=1)
+        S_, _, c, h, w = lat.shape
+        lat_nhwc = lat.reshape(S * n_cam, c, h, w).permute(0, 2, 3, 1).contiguous().view(-1, c)
+        V = S * n_cam * (2 if cfg else 1)
+        st = dict(ue=un.engine(), ce=cn.engine(), V=V, h=h, w=w, S=S, n_cam=n_cam, cfg=cfg,
+                  guidance=float(guidance_scale), cond_scale=float(controlnet_conditioning_scale), latents=lat_nhwc,
+                  c_kv=cond["kv"], u_kv=u_kv, lc=lc, map=cond["map"],
+                  t_dev=torch.zeros(V, dtype=F32, device=dev), coef_dev=torch.zeros(2, dtype=F32, device=dev))
+        return st
+
+    def _set_step(self, st, i):
+        st["t_dev"].copy_(st["t_table"][i], non_blocking=True)
+        st["coef_dev"].copy_(st["coef_table"][i], non_blocking=True)
+
+    def set_schedule(self, st, num_inference_steps):
+        ts = self.scheduler.set_timesteps(num_inference_steps)
+        dev = st["latents"].device
+        st["t_table"] = torch.tensor(ts, dtype=F32, device=dev)[:, None].expand(-1, st["V"]).contiguous()
+        st["coef_table"] = torch.tensor(self.scheduler.coefs, dtype=F32, device=dev)
+        return ts
+
+    def run_steps(self, st, first: int, last: int):
+        """Run denoising steps [first, last) on the resident state (eager on the first use, then graph replay)."""
+        key = (st["V"], st["h"], st["w"], st["cfg"], st["lc"], id(st["latents"]))
+        for i in range(first, last):
+            self._set_step(st, i)
+            if not self.use_cuda_graph:
+                self._step(st)
+                continue
+            if self._graph is None or self._graph_key != key:
+                # one eager step sizes workspaces / sets kernel attributes, then capture the same step
+                saved = st["latents"].clone()
+                self._step(st)
+                st["latents"].copy_(saved)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step(st)
+                st["latents"].copy_(saved)
+                self._graph, self._graph_key, self._graph_state = g, key, st
+            self._graph.replay()
+
+    @torch.no_grad()
+    def __call__(self, image, camera_param, prompt_embeds, negative_prompt_embeds=None, latents=None,
+                 num_inference_steps: int = 50, guidance_scale: float = 2.0, bev_controlnet_kwargs: Optional[Dict] = None,
+                 controlnet_conditioning_scale: float = 1.0, output_type: str = "latent"):
+        """Same argument meaning as the reference pipeline call (:114-160).  Returns latents (S, n_cam, 4, h, w) fp32."""
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
+        boxes = (bev_controlnet_kwargs or {}).get("bboxes_3d_data")
+        st = self.prepare(latents, prompt_embeds, negative_prompt_embeds, camera_param, boxes, image, guidance_scale,
+                          controlnet_conditioning_scale)
+        self.set_schedule(st, num_inference_steps)
+        self._graph = None  # state buffers are new
+        self.run_steps(st, 0, num_inference_steps)
+        return self.latents_out(st)
+
+    @staticmethod
+    def latents_out(st):
+        S, n_cam, h, w = st["S"], st["n_cam"], st["h"], st["w"]
+        return st["latents"].view(S, n_cam, h, w, -1).permute(0, 1, 4, 2, 3).contiguous()
