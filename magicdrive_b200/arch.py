@@ -323,7 +323,11 @@ def synthetic_state_dict(shapes, seed: int = 0, scale: float = 1.0):
         rng = np.random.Generator(np.random.Philox(key=(seed << 32) + zlib.crc32(name.encode())))
         if name.endswith(".weight") and len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
-            a = rng.standard_normal(shape, dtype=np.float32) * (scale / np.sqrt(fan_in))
+            # the camera / box encoders see raw metric inputs (fx ~ 1.27e3 px, box corners +-50 m); a trained
+            # checkpoint keeps their tokens O(1-10) like the CLIP tokens beside them, so do the synthetic weights
+            # (otherwise one token saturates every conditioning softmax and bf16 parity becomes a coin flip)
+            gain = {"cam2token.weight": 0.02, "bbox_embedder.bbox_proj.weight": 0.1}.get(name, 1.0)
+            a = rng.standard_normal(shape, dtype=np.float32) * (gain * scale / np.sqrt(fan_in))
         elif name.endswith(".weight"):  # norm gains
             a = 1.0 + 0.1 * rng.standard_normal(shape, dtype=np.float32)
         elif "_class_tokens" in name:

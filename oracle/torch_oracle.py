@@ -101,7 +101,8 @@ def transformer_block(sd: SD, p: str, x, ctx, heads, multiview: bool, neighbors=
     """BasicTransformerBlock.forward (attention.py:123-182) / BasicMultiviewTransformerBlock.forward
     (magicdrive/networks/blocks.py:144-238, 'add' mode of _construct_attn_input :112-121)."""
     x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x), None, heads)
-    x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), ctx, heads)
+    if (p + ".attn2.to_q.weight") in sd:  # absent only in the cross_attention_dim=None known-answer test
+        x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), ctx, heads)
     if multiview:
         n_cam = len(neighbors)
         h = _ln(sd, p + ".norm4", x)

@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, checkpoint-name
+compatibility with the reference, host helpers mirroring the reference's pipeline-facing methods."""
+import ctypes
+import json
+import os
+import re
+from dataclasses import asdict
+
+import pytest
+import torch
+
+from magicdrive_b200 import _lib, arch
+from magicdrive_b200.models import BEVControlNetModel, UNet2DConditionModelMultiview
+from tests.common import GOLDEN, tiny_configs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "magicdrive_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 18
+    L = _lib.lib()  # raises if the .so is missing
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/magicdrive_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
+    assert L.mdb_version() >= 100
+    assert L.mdb_device_ok() in (0, 1)
+
+
+def test_gemm_desc_layout_matches_header():
+    # field order / count of the ctypes mirror vs the C struct
+    src = open(os.path.join(ROOT, "include", "magicdrive_b200.h")).read()
+    body = src[src.index("typedef struct {"):src.index("} mdb_gemm_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for decl in body.split(";"):
+        decl = decl.replace("typedef struct {", "").strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            c_fields.append(part.replace("*", " ").split()[-1])
+    assert c_fields == [f[0] for f in _lib.GemmDesc._fields_]
+
+
+def test_errors_are_reported_not_swallowed():
+    L = _lib.lib()
+    d = _lib.GemmDesc()
+    rc = L.mdb_gemm_conv(ctypes.byref(d), None)
+    assert rc != 0 and b"null pointer" in L.mdb_last_error()
+    assert L.mdb_attention(None, 8, None, 8, None, 8, None, 8, 1, 1, 1, 1, 40, None, 1, 1.0, None) != 0
+
+
+@pytest.mark.parametrize("name", ["sd15", "tiny"])
+def test_parameter_names_match_reference_checkpoints(name):
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[name]
+    u, c = (arch.UNetConfig(), arch.ControlNetConfig()) if name == "sd15" else tiny_configs()
+    assert {k: list(v) for k, v in arch.unet_param_shapes(u).items()} == ref["unet"]
+    assert {k: list(v) for k, v in arch.controlnet_param_shapes(c).items()} == ref["controlnet"]
+
+
+def test_modules_state_dict_roundtrip_and_no_cpu_fallback():
+    u, c = tiny_configs()
+    un = UNet2DConditionModelMultiview(**asdict(u))
+    cn = BEVControlNetModel(**asdict(c))
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))["tiny"]
+    assert {k: list(v.shape) for k, v in un.state_dict().items()} == ref["unet"]
+    assert {k: list(v.shape) for k, v in cn.state_dict().items()} == ref["controlnet"]
+    sd = arch.synthetic_state_dict(arch.unet_param_shapes(u), 3)
+    un.load_state_dict(sd)
+    assert all(torch.equal(un.state_dict()[k], v) for k, v in sd.items())
+    assert un.config.in_channels == 4 and un.dtype == torch.float32
+    with pytest.raises(_lib.MdbError):
+        un(torch.zeros(6, 4, 10, 13), 5, torch.zeros(6, 10, 768))  # CPU tensors: must fail loudly, never fall back
+    # zero-initialised modules of the reference must NOT be zero in the synthetic weights
+    for k in ("down_blocks.0.attentions.0.transformer_blocks.0.connector.weight",):
+        assert sd[k].abs().sum() > 0
+
+
+def test_uncond_helpers_match_reference_fixture():
+    e = torch.load(os.path.join(GOLDEN, "tiny_encoders.pt"), weights_only=False)
+    _, c = tiny_configs()
+    cn = BEVControlNetModel(**asdict(c))
+    cn.load_state_dict(arch.synthetic_state_dict(arch.controlnet_param_shapes(c), e["seed"] + 1))
+    assert torch.equal(cn.uncond_cam_param([2, 6]), e["uncond_cam"])
+    cam = e["camera_param"]
+    boxes = {k: v.reshape(1, 6, *v.shape[1:]) for k, v in e["boxes"].items()}
+    kw = cn.add_uncond_to_kwargs(camera_param=cam, bboxes_3d_data=boxes, image=torch.zeros(1, 8, 4, 4), max_len=9)
+    assert kw["camera_param"].shape == (2, 6, 3, 7) and torch.equal(kw["camera_param"][1], cam[0])
+    assert kw["bboxes_3d_data"]["bboxes"].shape == (2, 6, 9, 8, 3)
+    assert not kw["bboxes_3d_data"]["masks"][0].any() and kw["bboxes_3d_data"]["masks"].dtype == torch.bool
+    assert torch.equal(kw["bboxes_3d_data"]["classes"][1, :, :5], boxes["classes"][0])
