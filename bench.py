@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-view denoising hot path (BASELINE.json: "6-view 224x400 denoising-steps/sec").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cam|full] [--scenes S]
+
+One "step" = ControlNet forward + multi-view UNet forward + classifier-free-guidance combine + DDIM update for S
+six-view scenes per GPU (CFG on: 12 view-samples per scene-step, the reference default guidance_scale = 2).
+N > 1 (torchrun, one process per GPU): scenes are sharded across ranks, no data-path collective ("weak" scaling);
+time = max over ranks of the device-timed loop, value = all scene-steps / time.
+`--impl reference` times the reference's CPU arithmetic (the fp32 oracle port, torch CPU kernels, all host threads)
+on the same workload, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TFLOP_PER_SCENE_STEP_CFG = {"224x400": 4.75, "424x800": 24.0}  # BASELINE.md §2 (algorithmic, CFG on)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cam", choices=["cam", "full"],
+                    help="cam = configs[1] (text + camera conditioning); full = configs[2] (+ 20 boxes/view + BEV map)")
+    ap.add_argument("--scenes", type=int, default=1, help="six-view scenes per GPU")
+    ap.add_argument("--res", default="224x400", choices=["224x400", "424x800"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def make_inputs(args, rank):
+    from magicdrive_b200.synthetic import synthetic_inputs  # seeded input generator (no model arithmetic)
+    h, w = (28, 50) if args.res == "224x400" else (53, 100)
+    mhw = 200 if args.res == "224x400" else 400
+    inp = synthetic_inputs(args.scenes, 6, h, w, n_box=20 if args.workload == "full" else 0, map_hw=mhw,
+                           seed=args.seed + 1000 * rank)
+    if args.workload == "cam":
+        inp["bev_map"] = torch.zeros_like(inp["bev_map"])  # configs[1]: no map / no boxes; the ControlNet still runs
+    return inp, h, w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference_cpu(args, steps, warmup):
+    """The reference's CPU path restated (oracle/torch_oracle.py, fp32, torch CPU kernels on all host threads)."""
+    from magicdrive_b200 import arch
+    from oracle import torch_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    ucfg, ccfg = arch.UNetConfig(), arch.ControlNetConfig(map_size=(8, 200, 200) if args.res == "224x400" else (8, 400, 400))
+    usd = arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), 11)
+    csd = arch.synthetic_state_dict(arch.controlnet_param_shapes(ccfg), 12)
+    inp, h, w = make_inputs(args, 0)
+    sched = O.DDIM()
+    ts = sched.set_timesteps(50).tolist()
+    cam, boxes = O.add_uncond_to_kwargs(csd, ccfg, inp["camera_param"], inp["bboxes_3d_data"])
+    text = torch.cat([inp["negative_prompt_embeds"], inp["prompt_embeds"]])
+    image = torch.cat([inp["bev_map"]] * 2)
+    lat = torch.stack([inp["latents"]] * 6, 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t = ts[i % len(ts)]
+            t0 = time.perf_counter()
+            x2 = torch.cat([lat] * 2)
+            tt = torch.full((x2.shape[0],), t, dtype=torch.int64)
+            down, mid, ctx = O.controlnet_forward(csd, ccfg, x2, tt, cam, boxes, text, image)
+            eps = O.unet_forward(usd, ucfg, x2.reshape(-1, *x2.shape[2:]), torch.tensor(t), ctx, down, mid)
+            eu, ec = eps.chunk(2)
+            eps = eu + 2.0 * (ec - eu)
+            lat = sched.step(eps, t, lat.reshape(-1, *lat.shape[2:])).reshape(lat.shape)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return args.scenes / sec, sec, torch.get_num_threads()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    config = {"workload": f"configs[{1 if args.workload == 'cam' else 2}]: 6-view {args.res}, "
+                          + ("text+camera-pose cond" if args.workload == "cam" else "full cond (20 boxes/view + BEV map + text)")
+                          + ", CFG 2.0 (12 view-samples per scene-step), DDIM eta=0, SD-1.5-config UNet + BEVControlNet, random-init weights",
+              "scenes_per_gpu": args.scenes, "views": 6, "latent_hw": [28, 50] if args.res == "224x400" else [53, 100],
+              "sharding": "scene-per-GPU replicas, no data-path collective",
+              "l2": "2.6 GB of weights are streamed every step (>> 126 MB L2), no explicit flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warm = min(args.steps, 3), min(args.warmup, 1)
+        val, sec, cores = run_reference_cpu(args, steps, warm)
+        sample = f"{steps} full scene-steps (CFG, V=12) after {warm} warm-up, fp32, torch CPU kernels"
+        line = {"impl": "reference", "metric": "6-view 224x400 denoising-steps/sec", "value": val, "unit": "scene-steps/s",
+                "n_gpus": n_gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "scene-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "scene-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from dataclasses import asdict
+
+    from magicdrive_b200 import arch, ops
+    from magicdrive_b200.models import BEVControlNetModel, UNet2DConditionModelMultiview
+    from magicdrive_b200.pipeline import BEVControlNetDenoiser
+
+    ucfg = arch.UNetConfig()
+    ccfg = arch.ControlNetConfig(map_size=(8, 200, 200) if args.res == "224x400" else (8, 400, 400))
+    un = UNet2DConditionModelMultiview(**asdict(ucfg)).reset_parameters_synthetic(11).to(dev, torch.bfloat16)
+    cn = BEVControlNetModel(**asdict(ccfg)).reset_parameters_synthetic(12).to(dev, torch.bfloat16)
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph)
+    inp, h, w = make_inputs(args, rank)
+    boxes = inp["bboxes_3d_data"]
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    if boxes is not None:
+        host["bboxes_3d_data"] = {k: v.pin_memory() for k, v in boxes.items()}
+
+    def prepare():
+        return pipe.prepare(host["latents"], host["prompt_embeds"], host["negative_prompt_embeds"], host["camera_param"],
+                            host["bboxes_3d_data"], host["bev_map"], guidance_scale=2.0)
+
+    st = prepare()
+    total = args.warmup + args.steps
+    pipe.set_schedule(st, 50)
+    sched_len = 50
+
+    def run(i):
+        pipe.run_steps(st, i % sched_len, i % sched_len + 1)
+
+    ops.reset_launch_count()
+    run(0)  # eager (sizes workspaces) + graph capture + first replay
+    launches_per_step = None
+    for i in range(1, args.warmup):
+        run(i)
+    # count launches of one step on an eager pass (graph replay launches the same nodes)
+    was = pipe.use_cuda_graph
+    pipe.use_cuda_graph = False
+    ops.reset_launch_count()
+    run(args.warmup)
+    launches_per_step = ops.launch_count() + 2  # + torch.cat of the CFG halves + f32->bf16 already counted; +2 = step-input copies
+    pipe.use_cuda_graph = was
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region (device-timed, CUDA events on the launching stream)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for i in range(args.steps):
+        run(args.warmup + 1 + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = tt.item()
+    ms_step = ms_total / args.steps
+    value = n_gpus * args.scenes / (ms_step * 1e-3)
+
+    # ---- end-to-end through the public call with HOST buffers: per step H2D of the scene's inputs (pinned),
+    #      conditioning re-encode, one denoising step, D2H of the latents
+    out_host = torch.empty((args.scenes, 6, 4, h, w), dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in [host["latents"], host["prompt_embeds"], host["negative_prompt_embeds"],
+                                                     host["camera_param"], host["bev_map"]])
+    if boxes is not None:
+        h2d += sum(v.numel() * v.element_size() for v in host["bboxes_3d_data"].values())
+    d2h = out_host.numel() * 4
+    for i in range(2):
+        s2 = prepare()
+        pipe.run_steps(s2, i, i + 1)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        s2 = prepare()
+        pipe.run_steps(s2, i % sched_len, i % sched_len + 1)
+        out_host.copy_(pipe.latents_out(s2), non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = tt.item()
+    e2e_value = n_gpus * args.scenes / (ms_e2e / args.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): per-launch CUDA events, eager pass
+    pipe.use_cuda_graph = False
+    st = prepare()
+    pipe.set_schedule(st, 50)
+    run(0)
+    ops.start_profile()
+    run(1)
+    prof = ops.stop_profile()
+    pipe.use_cuda_graph = was
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF/s sustained (of fallback)"
+    g = [(f, s) for k, f, s in prof if k == "gemm_conv"]
+    a = [(f, s) for k, f, s in prof if k == "attention"]
+    gf, gs = sum(f for f, _ in g), sum(s for _, s in g)
+    af, as_ = sum(f for f, _ in a), sum(s for _, s in a)
+    achieved = gf / gs / 1e12 if gs > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv, all shapes of one step)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
+                "launches": len(g), "flops_per_step": gf, "kernel_ms_per_step": gs * 1e3, "traffic": None,
+                "attention": {"achieved": (af / as_ / 1e12 if as_ > 0 else 0.0), "launches": len(a),
+                              "kernel_ms_per_step": as_ * 1e3, "flops_per_step": af},
+                "whole_step": {"algorithmic_tflop": TFLOP_PER_SCENE_STEP_CFG[args.res] * args.scenes,
+                               "achieved": TFLOP_PER_SCENE_STEP_CFG[args.res] * args.scenes / (ms_step * 1e-3),
+                               "frac": TFLOP_PER_SCENE_STEP_CFG[args.res] * args.scenes / (ms_step * 1e-3) / peak_tf}}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and n_gpus == 1:
+            v, sec, cores = run_reference_cpu(args, 1, 1)
+            cpu = {"value": v, "unit": "scene-steps/s", "cores": cores, "kind": "port",
+                   "sample": "1 full scene-step (CFG, V=12, ControlNet+UNet) after 1 warm-up, fp32, torch CPU kernels"}
+        line = {"metric": "6-view 224x400 denoising-steps/sec" if args.res == "224x400" else "6-view 424x800 denoising-steps/sec",
+                "value": value, "unit": "scene-steps/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "scene-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps,
+                        "note": "per step: pinned-host inputs -> device, conditioning re-encode, 1 denoising step, latents -> host"},
+                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "roofline": roofline, "cpu_baseline": cpu, "cuda_graph": not args.no_graph}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

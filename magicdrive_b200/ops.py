@@ -16,6 +16,35 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+_profile = None  # when a list: (kind, algorithmic flops, start event, end event) per tensor-core launch
+
+
+def start_profile():
+    """Bracket every tensor-core launch with CUDA events on the launching stream (eager mode only)."""
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(k, f, a.elapsed_time(b) * 1e-3) for k, f, a, b in rec]
+
+
+def _prof_begin():
+    if _profile is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(kind, flops, e0):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _profile.append((kind, flops, e0, e1))
 
 
 def launch_count() -> int:
@@ -99,7 +128,9 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
         d.workspace, d.workspace_bytes = None, 0
     d.force_block_n, d.force_splits = force_block_n, force_splits
     L = _lib.lib()
+    e0 = _prof_begin()
     check(L.mdb_gemm_conv(C.byref(d), _stream()), "mdb_gemm_conv")
+    _prof_end("gemm_conv", 2.0 * pixels * n_out * taps * taps * (c0 + c1), e0)
     _launches += L.mdb_gemm_conv_launches(C.byref(d))
     return out
 
@@ -137,7 +168,7 @@ def groupnorm(x0, c0, ld0, n_img, hw, gamma, beta, eps, silu, x1=None, c1=0, ld1
     stats = torch.empty((n_img * groups * 2,), dtype=F32, device=x0.device)
     check(_lib.lib().mdb_groupnorm(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n_img, hw, groups, float(eps), _ptr(gamma),
                                    _ptr(beta), int(silu), _ptr(out), c0 + c1, _ptr(stats), _stream()), "mdb_groupnorm")
-    _launches += 3  # memset node + stats + apply
+    _launches += 2  # stats + apply kernels (plus one memset node)
     return out
 
 
@@ -158,8 +189,10 @@ def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=No
     _need_cuda(q, k, v)
     if out is None:
         out = torch.empty((b * lq, heads * d), dtype=BF16, device=q.device)
+    e0 = _prof_begin()
     check(_lib.lib().mdb_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), out.stride(0), b, heads, lq, lk,
                                    d, _ptr(kv_index), n_sets, float(scale), _stream()), "mdb_attention")
+    _prof_end("attention", 4.0 * b * heads * lq * lk * d * n_sets, e0)
     _launches += 1
     return out
 
