@@ -67,6 +67,7 @@ typedef struct {
   size_t workspace_bytes;
   int force_block_n;    /* 0 = auto; test hook */
   int force_splits;     /* 0 = auto; test hook */
+  int kernel_variant;   /* 0 = persistent double-buffered kernel (default); 1 = one-tile-per-CTA kernel; test hook */
 } mdb_gemm_desc;
 
 int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream);

@@ -9,6 +9,7 @@
 #include "../../include/magicdrive_b200.h"
 #include "common_host.h"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 using namespace mdb;
 
@@ -182,6 +183,30 @@ int launch(const mdb_gemm_desc* d, const Plan& pl, const CUtensorMap& tA0, const
   return MDB_OK;
 }
 
+template <int BN>
+int launch2(const Plan& pl, const CUtensorMap& tA0, const CUtensorMap& tA1, const CUtensorMap& tB, const GemmParams& gp,
+            cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg2<BN>::kSmemBytes);
+    if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  GemmParams2 pp;
+  pp.p = gp;
+  pp.m_tiles = pl.tiles_n * pl.tiles_h * pl.tiles_w;
+  pp.n_tiles = pl.n_tiles;
+  pp.splits = pl.splits;
+  const long long total = (long long)pp.m_tiles * pp.n_tiles * pp.splits;
+  const int sms = num_sms();
+  const int grid = (int)(total < sms ? total : sms);
+  gemm_tc2_kernel<BN><<<grid, GemmCfg2<BN>::kThreads, GemmCfg2<BN>::kSmemBytes, st>>>(tA0, tA1, tB, pp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "gemm_tc2_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
+  return MDB_OK;
+}
+
 }  // namespace
 
 extern "C" int mdb_gemm_conv_launches(const mdb_gemm_desc* d) {
@@ -226,6 +251,15 @@ extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
   gp.out = d->out, gp.ldo = d->ldo, gp.out_scale = d->out_scale;
   gp.partial = static_cast<float*>(d->workspace);
 
+  if (d->kernel_variant != 1) {
+    switch (pl.block_n) {
+      case 256: rc = launch2<256>(pl, tA0, tA1, tB, gp, st); break;
+      case 160: rc = launch2<160>(pl, tA0, tA1, tB, gp, st); break;
+      case 128: rc = launch2<128>(pl, tA0, tA1, tB, gp, st); break;
+      case 64: rc = launch2<64>(pl, tA0, tA1, tB, gp, st); break;
+      default: return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: unsupported block_n %d", pl.block_n);
+    }
+  } else
   switch (pl.block_n) {
     case 256: rc = launch<256>(d, pl, tA0, tA1, tB, gp, st); break;
     case 160: rc = launch<160>(d, pl, tA0, tA1, tB, gp, st); break;

@@ -15,6 +15,7 @@ from ._lib import GemmDesc, check
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+GEMM_VARIANT = int(__import__('os').environ.get('MDB_GEMM_VARIANT', '0'))  # test/bench hook: 1 = non-persistent kernel
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 _profile = None  # when a list: (kind, algorithmic flops, start event, end event) per tensor-core launch
 
@@ -25,11 +26,13 @@ def start_profile():
     _profile = []
 
 
-def stop_profile():
+def stop_profile(with_info: bool = False):
     global _profile
     rec, _profile = _profile, None
     torch.cuda.synchronize()
-    return [(k, f, a.elapsed_time(b) * 1e-3) for k, f, a, b in rec]
+    if with_info:
+        return [(k, f, a.elapsed_time(b) * 1e-3, info) for k, f, a, b, info in rec]
+    return [(k, f, a.elapsed_time(b) * 1e-3) for k, f, a, b, _ in rec]
 
 
 def _prof_begin():
@@ -40,11 +43,11 @@ def _prof_begin():
     return e
 
 
-def _prof_end(kind, flops, e0):
+def _prof_end(kind, flops, e0, info=""):
     if e0 is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        _profile.append((kind, flops, e0, e1))
+        _profile.append((kind, flops, e0, e1, info))
 
 
 def launch_count() -> int:
@@ -91,7 +94,8 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
               bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, ldr: int = 0, out: Optional[torch.Tensor] = None,
               ldo: Optional[int] = None, out_f32: bool = False, out_scale: float = 1.0, geglu: bool = False,
-              force_block_n: int = 0, force_splits: int = 0, allow_split_k: bool = True) -> torch.Tensor:
+              force_block_n: int = 0, force_splits: int = 0, allow_split_k: bool = True,
+              kernel_variant: int = 0) -> torch.Tensor:
     """tcgen05 GEMM / implicit-GEMM conv (mdb_gemm_conv).  `a0` (and `a1`) are NHWC bf16 buffers whose pixel
     stride is lda* elements; `w` is bf16 [n_out, taps*taps*(c0+c1)]."""
     global _launches
@@ -127,10 +131,13 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
     else:
         d.workspace, d.workspace_bytes = None, 0
     d.force_block_n, d.force_splits = force_block_n, force_splits
+    d.kernel_variant = kernel_variant or GEMM_VARIANT
     L = _lib.lib()
     e0 = _prof_begin()
     check(L.mdb_gemm_conv(C.byref(d), _stream()), "mdb_gemm_conv")
-    _prof_end("gemm_conv", 2.0 * pixels * n_out * taps * taps * (c0 + c1), e0)
+    _prof_end("gemm_conv", 2.0 * pixels * n_out * taps * taps * (c0 + c1), e0,
+              f"M={pixels} N={n_out} K={taps * taps * (c0 + c1)} img={n_img}x{h_out}x{w_out} taps={taps} s={stride} "
+              f"geglu={int(geglu)} res={int(residual is not None)}")
     _launches += L.mdb_gemm_conv_launches(C.byref(d))
     return out
 
@@ -192,7 +199,7 @@ def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=No
     e0 = _prof_begin()
     check(_lib.lib().mdb_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), out.stride(0), b, heads, lq, lk,
                                    d, _ptr(kv_index), n_sets, float(scale), _stream()), "mdb_attention")
-    _prof_end("attention", 4.0 * b * heads * lq * lk * d * n_sets, e0)
+    _prof_end("attention", 4.0 * b * heads * lq * lk * d * n_sets, e0, f"B={b} H={heads} Lq={lq} Lk={lk} D={d} sets={n_sets}")
     _launches += 1
     return out
 

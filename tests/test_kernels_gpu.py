@@ -28,19 +28,20 @@ def _conv_weight(wt):  # [co, ci, kh, kw] -> [co, kh*kw*ci] (tap-major, channel-
     return wt.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous()
 
 
+@pytest.mark.parametrize("variant", [0, 1])  # 0 = persistent double-buffered kernel, 1 = one tile per CTA
 @pytest.mark.parametrize("bn", [0, 64, 128, 160, 256])
-@pytest.mark.parametrize("m,k,n", [(1000, 320, 320), (128, 64, 640), (336, 1280, 1280)])
-def test_gemm_plain(cuda_lib, bn, m, k, n):
+@pytest.mark.parametrize("m,k,n", [(1000, 320, 320), (128, 64, 640), (336, 1280, 1280), (16800, 320, 960)])
+def test_gemm_plain(cuda_lib, bn, m, k, n, variant):
     g = torch.Generator(device="cuda").manual_seed(1)
     x = _bf(torch.randn(m, k, device="cuda", generator=g))
     w = _bf(torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k))
     b = torch.randn(n, device="cuda", generator=g)
     r = _bf(torch.randn(m, n, device="cuda", generator=g))
     ref = x.float() @ w.float().t() + b + r.float()
-    out = ops.linear(x, w, bias=b, residual=r, out_f32=True, force_block_n=bn, allow_split_k=False)
+    out = ops.linear(x, w, bias=b, residual=r, out_f32=True, force_block_n=bn, allow_split_k=False, kernel_variant=variant)
     torch.cuda.synchronize()
     assert _rel(out, ref) < 2e-5, _rel(out, ref)
-    out16 = ops.linear(x, w, bias=b, residual=r, force_block_n=bn, allow_split_k=False)
+    out16 = ops.linear(x, w, bias=b, residual=r, force_block_n=bn, allow_split_k=False, kernel_variant=variant)
     assert _rel(out16, ref) < 6e-3
 
 
@@ -73,8 +74,10 @@ def test_gemm_strided_views(cuda_lib):
 @pytest.mark.parametrize("n,h,w,ci,co,stride", [
     (3, 28, 50, 320, 320, 1), (2, 14, 25, 640, 1280, 1), (5, 4, 7, 1280, 1280, 1), (3, 7, 13, 1280, 640, 1),
     (2, 28, 50, 320, 320, 2), (3, 14, 25, 640, 640, 2), (5, 7, 13, 1280, 1280, 2), (1, 53, 100, 320, 320, 1),
+    (12, 28, 50, 320, 320, 1),
 ])
-def test_conv3x3(cuda_lib, n, h, w, ci, co, stride):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_conv3x3(cuda_lib, n, h, w, ci, co, stride, variant):
     g = torch.Generator(device="cuda").manual_seed(4)
     x = _bf(torch.randn(n, ci, h, w, device="cuda", generator=g))
     wt = _bf(torch.randn(co, ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * ci))
@@ -83,7 +86,7 @@ def test_conv3x3(cuda_lib, n, h, w, ci, co, stride):
     ref = F.conv2d(x.float(), wt.float(), b, stride=stride, padding=1) + temb[:, :, None, None]
     ho, wo = ref.shape[-2:]
     out = ops.gemm_conv(_nhwc(x), _conv_weight(wt), n_img=n, h_in=h, w_in=w, c0=ci, lda0=ci, n_out=co, taps=3,
-                        stride=stride, pad=1, bias=b, rowbias=temb, out_f32=True)
+                        stride=stride, pad=1, bias=b, rowbias=temb, out_f32=True, kernel_variant=variant)
     assert out.shape == (n * ho * wo, co)
     assert _rel(out, _nhwc(ref)) < 3e-5, _rel(out, _nhwc(ref))
 
