@@ -128,11 +128,17 @@ int mdb_nhwc_to_nchw(const void* x_bf16, int n, int c, int h, int w, void* out, 
 int mdb_f32_to_bf16(const float* x, void* out, long long n, void* stream);
 int mdb_bf16_to_f32(const void* x, float* out, long long n, void* stream);
 
+/* Latents [pix, cin] (fp32 or bf16) -> bf16 [repeat*pix, cpad] with channels >= cin zeroed: the K-padded A operand
+ * that lets conv_in (unet_2d_condition.py:231, 4 -> 320 channels) run on the tensor-core path; repeat = 2 duplicates
+ * the batch for classifier-free guidance (pipeline_bev_controlnet.py:352-354). */
+int mdb_pack_latents(const void* x, int x_is_f32, long long pix, int cin, int cpad, int repeat, void* out, void* stream);
+
 /* Classifier-free guidance + DDIM (eta = 0) update fused (pipeline_bev_controlnet.py:426-436;
- * scheduling_ddim.py:325-445).  eps: fp32 [2, n] (uncond ; cond) or [1, n] if !cfg.  coef: device fp32[2] =
- * {sqrt(abar_prev/abar_t), sqrt(1-abar_prev) - sqrt(abar_prev*(1-abar_t)/abar_t)} so x_prev = c0*x + c1*eps. */
-int mdb_cfg_ddim_step(const float* eps, int cfg, float guidance, const float* coef, float* latents, long long n,
-                      void* stream);
+ * scheduling_ddim.py:325-445).  eps: fp32 [(2 if cfg else 1) * n/c pixels, eps_ld] (uncond half first), c channels
+ * used per pixel.  coef: device fp32[2] = {sqrt(abar_prev/abar_t), sqrt(1-abar_prev) - sqrt(abar_prev*(1-abar_t)/abar_t)}
+ * so x_prev = c0*x + c1*eps.  latents: fp32 [n/c, c] updated in place. */
+int mdb_cfg_ddim_step(const float* eps, int eps_ld, int c, int cfg, float guidance, const float* coef, float* latents,
+                      long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,8 @@ SIGNATURES = {
     "mdb_nhwc_to_nchw": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "mdb_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "mdb_bf16_to_f32": (_i, [_vp, _vp, _ll, _vp]),
-    "mdb_cfg_ddim_step": (_i, [_vp, _i, _f, _vp, _vp, _ll, _vp]),
+    "mdb_pack_latents": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
+    "mdb_cfg_ddim_step": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _ll, _vp]),
 }
 
 

@@ -2,6 +2,7 @@
 // 16-byte vector loads along the contiguous channel axis, fp32 statistics, warp-shuffle / smem reductions.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/magicdrive_b200.h"
 #include "common_host.h"
@@ -114,6 +115,98 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, in
   }
 }
 
+// ---- GroupNorm, single kernel: one CTA per (image, group).  The group's hw x cpg slab (a few tens of KB, L2-resident:
+// it was just written by the producing GEMM) is read once into registers, mean and variance are computed exactly
+// (two-pass over the register copy), then normalise + affine (+SiLU) and store.  No atomics, no memset, no stats buffer.
+constexpr int GN_CACHE = 56;  // bf16x2 units cached per thread
+template <int T>
+__global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0,
+                                                     const __nv_bfloat16* __restrict__ x1, int c1, int ld1, int hw,
+                                                     int groups, float eps, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, int silu,
+                                                     __nv_bfloat16* __restrict__ out, int ldo) {
+  __shared__ float red[T / 32];
+  __shared__ float bcast;
+  const int g = blockIdx.x, img = blockIdx.y;
+  const int ctot = c0 + c1;
+  const int cpg = ctot / groups;
+  const int pp = cpg >> 1;  // bf16x2 units per pixel
+  const int units = hw * pp;
+  const int cbase = g * cpg;
+  const long long pix0 = static_cast<long long>(img) * hw;
+  auto src = [&](int u) -> const uint32_t* {
+    const int p = u / pp, c = cbase + 2 * (u - p * pp);
+    return (c < c0) ? reinterpret_cast<const uint32_t*>(x0 + (pix0 + p) * ld0 + c)
+                    : reinterpret_cast<const uint32_t*>(x1 + (pix0 + p) * ld1 + (c - c0));
+  };
+  auto block_sum = [&](float v) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = (threadIdx.x < T / 32) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) bcast = t;
+    }
+    __syncthreads();
+    return bcast;
+  };
+  uint32_t cache[GN_CACHE];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) {
+    const int u = threadIdx.x + k * T;
+    if (u < units) {
+      cache[k] = __ldg(src(u));
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
+      s += f.x + f.y;
+    }
+  }
+  for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) {
+    const uint32_t w = __ldg(src(u));
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+    s += f.x + f.y;
+  }
+  const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  const float mean = block_sum(s) * inv_cnt;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) {
+    const int u = threadIdx.x + k * T;
+    if (u < units) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
+      sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+    }
+  }
+  for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) {
+    const uint32_t w = __ldg(src(u));
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+    sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+  }
+  const float rstd = rsqrtf(block_sum(sq) * inv_cnt + eps);
+  auto emit = [&](int u, uint32_t w) {
+    const int p = u / pp, c = cbase + 2 * (u - p * pp);
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+    float y0 = (f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    float y1 = (f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+    if (silu) {
+      y0 = y0 / (1.0f + __expf(-y0));
+      y1 = y1 / (1.0f + __expf(-y1));
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+    *reinterpret_cast<uint32_t*>(out + (pix0 + p) * ldo + c) = *reinterpret_cast<uint32_t*>(&h);
+  };
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) {
+    const int u = threadIdx.x + k * T;
+    if (u < units) emit(u, cache[k]);
+  }
+  for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) emit(u, __ldg(src(u)));
+}
+
 // ---- LayerNorm: one warp per row, values kept in registers (two-pass mean / variance like ATen).
 template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, int ldx,
@@ -184,6 +277,19 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
                      groups);
   if (c1 > 0 && !x1) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: c1>0 but x1 null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (((ctot / groups) & 1) == 0 && (c0 & 1) == 0 && !getenv("MDB_GN_TWO_KERNEL")) {
+    const long long units = static_cast<long long>(hw) * (ctot / groups / 2);
+    if (units <= 256LL * GN_CACHE)
+      gn_fused_kernel<256><<<dim3(groups, n_img), 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
+          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo);
+    else
+      gn_fused_kernel<1024><<<dim3(groups, n_img), 1024, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
+          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo);
+    MDB_CHECK_LAUNCH("gn_fused_kernel");
+    return MDB_OK;
+  }
   cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * n_img * groups, st);
   if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "mdb_groupnorm memset: %s", cudaGetErrorString(e));
   const int vpp = ctot / 8;

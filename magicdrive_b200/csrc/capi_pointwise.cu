@@ -234,15 +234,31 @@ __global__ void conv_direct_kernel(const TI* __restrict__ x, int n, int h, int w
 }
 
 __global__ void cfg_ddim_kernel(const float* __restrict__ eps, int cfg, float guidance, const float* __restrict__ coef,
-                                float* __restrict__ lat, long long n) {
+                                float* __restrict__ lat, long long n, int c, int eps_ld) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float e = eps[i];
+  const long long pix = i / c;
+  const int ch = static_cast<int>(i - pix * c);
+  const long long npix = n / c;
+  float e = eps[pix * eps_ld + ch];
   if (cfg) {
-    const float ec = eps[n + i];
+    const float ec = eps[(npix + pix) * eps_ld + ch];
     e = e + guidance * (ec - e);
   }
   lat[i] = coef[0] * lat[i] + coef[1] * e;
+}
+
+// latents [pix, cin] (fp32 or bf16) -> bf16 [repeat * pix, cpad], channels >= cin zero: the K-padded A operand of the
+// tensor-core conv_in; `repeat` = 2 duplicates the batch for classifier-free guidance ([uncond ; cond] share latents)
+template <typename TI>
+__global__ void pack_latents_kernel(const TI* __restrict__ x, long long pix, int cin, int cpad, int repeat,
+                                    __nv_bfloat16* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pix * cpad) return;
+  const long long p = i / cpad;
+  const int c = static_cast<int>(i - p * cpad);
+  const __nv_bfloat16 v = (c < cin) ? __float2bfloat16_rn(ldf(x + p * cin + c)) : __float2bfloat16_rn(0.f);
+  for (int r = 0; r < repeat; ++r) out[(r * pix + p) * cpad + c] = v;
 }
 
 inline unsigned nblocks(long long n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
@@ -364,10 +380,27 @@ extern "C" int mdb_conv_direct(const void* x, int x_is_f32, int n, int h, int w,
   return MDB_OK;
 }
 
-extern "C" int mdb_cfg_ddim_step(const float* eps, int cfg, float guidance, const float* coef, float* latents, long long n,
-                                 void* stream) {
+extern "C" int mdb_pack_latents(const void* x, int x_is_f32, long long pix, int cin, int cpad, int repeat, void* out,
+                                void* stream) {
+  if (!x || !out) return set_error(MDB_ERR_INVALID, "mdb_pack_latents: null pointer");
+  if (cpad < cin || repeat < 1) return set_error(MDB_ERR_INVALID, "mdb_pack_latents: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_f32)
+    pack_latents_kernel<float><<<nblocks(pix * cpad, 256), 256, 0, st>>>(static_cast<const float*>(x), pix, cin, cpad, repeat,
+                                                                         static_cast<__nv_bfloat16*>(out));
+  else
+    pack_latents_kernel<__nv_bfloat16><<<nblocks(pix * cpad, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), pix, cin, cpad, repeat, static_cast<__nv_bfloat16*>(out));
+  MDB_CHECK_LAUNCH("pack_latents_kernel");
+  return MDB_OK;
+}
+
+extern "C" int mdb_cfg_ddim_step(const float* eps, int eps_ld, int c, int cfg, float guidance, const float* coef,
+                                 float* latents, long long n, void* stream) {
   if (!eps || !coef || !latents) return set_error(MDB_ERR_INVALID, "mdb_cfg_ddim_step: null pointer");
-  cfg_ddim_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, cfg, guidance, coef, latents, n);
+  if (c <= 0 || eps_ld < c || n % c) return set_error(MDB_ERR_INVALID, "mdb_cfg_ddim_step: bad shape");
+  cfg_ddim_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, cfg, guidance, coef, latents, n, c,
+                                                                                  eps_ld);
   MDB_CHECK_LAUNCH("cfg_ddim_kernel");
   return MDB_OK;
 }

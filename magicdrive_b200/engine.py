@@ -64,6 +64,28 @@ class _Weights:
             self.t[p + ".b"] = _f32(self.raw(p + ".bias"))
         return self.t[p + ".wd"], self.t[p + ".b"]
 
+    def conv_k_padded(self, p, cpad):
+        """3x3 filter with the input channels zero-padded to `cpad` (conv_in: 4 -> 64 so K is a whole 64-block)."""
+        if p + ".wk" not in self.t:
+            w = self.raw(p + ".weight").float()
+            wp = torch.zeros((w.shape[0], cpad, w.shape[2], w.shape[3]), dtype=F32, device=w.device)
+            wp[:, : w.shape[1]] = w
+            self.t[p + ".wk"] = pack_conv_weight(wp)
+            self.t[p + ".b"] = _f32(self.raw(p + ".bias"))
+        return self.t[p + ".wk"], self.t[p + ".b"]
+
+    def conv_n_padded(self, p, npad):
+        """3x3 filter with the output channels zero-padded to `npad` (conv_out: 4 -> 8, the kernel's N granularity)."""
+        if p + ".wn" not in self.t:
+            w = self.raw(p + ".weight").float()
+            wp = torch.zeros((npad, *w.shape[1:]), dtype=F32, device=w.device)
+            wp[: w.shape[0]] = w
+            bp = torch.zeros((npad,), dtype=F32, device=w.device)
+            bp[: w.shape[0]] = self.raw(p + ".bias").float()
+            self.t[p + ".wn"] = pack_conv_weight(wp)
+            self.t[p + ".bn"] = bp
+        return self.t[p + ".wn"], self.t[p + ".bn"]
+
     def lin(self, p, bias=True):
         if p + ".w" not in self.t:
             self.t[p + ".w"] = _bf(self.raw(p + ".weight"))
@@ -267,11 +289,15 @@ class _Net:
         x = self.resnet(r1, x, temb_all)
         return x, skips
 
-    def conv_in(self, x_nhwc: torch.Tensor, n, h, w, residual=None) -> FMap:
-        wd, b = self.W.conv_direct("conv_in")
+    CIN_PAD = 64  # latent channels are zero-padded to one 64-wide K block so conv_in runs on the tensor-core path
+
+    def conv_in(self, x_pad: torch.Tensor, n, h, w, residual=None) -> FMap:
+        """x_pad: [n*h*w, 64] bf16 (ops.pack_latents); optional residual [n*h*w, C0] (the BEV-map embedding)."""
+        wk, b = self.W.conv_k_padded("conv_in", self.CIN_PAD)
         c0 = self.cfg.block_out_channels[0]
-        out = ops.conv_direct(x_nhwc, wd, b, n=n, h=h, w=w, cin=self.cfg.in_channels, cout=c0, k=3, residual=residual)
-        return FMap(out.view(n * h * w, c0), n, h, w, c0)
+        out = ops.gemm_conv(x_pad, wk, n_img=n, h_in=h, w_in=w, c0=self.CIN_PAD, lda0=self.CIN_PAD, n_out=c0, taps=3,
+                            pad=1, bias=b, residual=residual, ldr=c0)
+        return FMap(out, n, h, w, c0)
 
 
 class UNetEngine(_Net):
@@ -284,12 +310,16 @@ class UNetEngine(_Net):
         self.transformers += [tr for b in self.up for _, tr in b.layers if tr]
         self._finalize_specs()
 
-    def forward(self, latents_nhwc: torch.Tensor, n, h, w, t_f32, ctx_kv, lc, down_res: Optional[List[torch.Tensor]] = None,
-                mid_res: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """latents [n*h*w, 4] bf16 -> predicted noise fp32 NHWC [n, h, w, out_channels]."""
+    COUT_PAD = 8
+
+    def forward(self, latents_pad: torch.Tensor, n, h, w, t_f32, ctx_kv, lc, down_res: Optional[List[torch.Tensor]] = None,
+                mid_res: Optional[torch.Tensor] = None, temb_all: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """latents [n*h*w, 64] bf16 (channel-padded) -> predicted noise fp32 [n*h*w, 8] (first out_channels valid).
+        `temb_all` may carry precomputed time-embedding projections ([1 or n, sum(cout)] fp32)."""
         cfg = self.cfg
-        temb_all = self.time_embed(t_f32)
-        x = self.conv_in(latents_nhwc, n, h, w)
+        if temb_all is None:
+            temb_all = self.time_embed(t_f32)
+        x = self.conv_in(latents_pad, n, h, w)
         x, skips = self.encoder(x, temb_all, ctx_kv, lc)
         if down_res is not None:
             skips = [FMap(ops.add(s.data, r), s.n, s.h, s.w, s.c) for s, r in zip(skips, down_res)]
@@ -309,8 +339,9 @@ class UNetEngine(_Net):
                 x = FMap(out, x.n, tgt.h, tgt.w, x.c)
         g, b = self.W.norm("conv_norm_out")
         hn = ops.groupnorm(x.data, x.c, x.c, x.n, x.h * x.w, g, b, cfg.norm_eps, True, groups=cfg.norm_num_groups)
-        wd, bo = self.W.conv_direct("conv_out")
-        return ops.conv_direct(hn, wd, bo, n=x.n, h=x.h, w=x.w, cin=x.c, cout=cfg.out_channels, k=3, out_f32=True)
+        wn, bo = self.W.conv_n_padded("conv_out", self.COUT_PAD)
+        return ops.gemm_conv(hn, wn, n_img=x.n, h_in=x.h, w_in=x.w, c0=x.c, lda0=x.c, n_out=self.COUT_PAD, taps=3, pad=1,
+                             bias=bo, out_f32=True)
 
 
 class ControlNetEngine(_Net):
@@ -390,12 +421,13 @@ class ControlNetEngine(_Net):
         return x  # bf16 [b, h, w, 320]
 
     # ---------------------------------------------------------------- per-step
-    def forward(self, latents_nhwc, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view: torch.Tensor,
-                conditioning_scale: float = 1.0):
-        """latents [n*h*w, 4] bf16 (n = scenes*views); t_f32 [n]; map_emb_per_view [n, h, w, 320] bf16.
+    def forward(self, latents_pad, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view: torch.Tensor,
+                conditioning_scale: float = 1.0, temb_all: Optional[torch.Tensor] = None):
+        """latents [n*h*w, 64] bf16 channel-padded (n = scenes*views); t_f32 [n]; map_emb_per_view [n, h, w, 320] bf16.
         Returns (12 + 1 residual maps as [pixels, C] bf16 tensors)."""
-        temb_all = self.time_embed(t_f32)
-        x = self.conv_in(latents_nhwc, n, h, w, residual=map_emb_per_view)
+        if temb_all is None:
+            temb_all = self.time_embed(t_f32)
+        x = self.conv_in(latents_pad, n, h, w, residual=map_emb_per_view)
         x, skips = self.encoder(x, temb_all, ctx_kv, lc)
         down = []
         for i, s in enumerate(skips):

@@ -200,15 +200,16 @@ class UNet2DConditionModelMultiview(_B200Module):
         if n % self.arch_cfg.n_cam:
             raise ValueError(f"batch {n} is not a multiple of the {self.arch_cfg.n_cam} camera views")
         ctx_kv, lc = self.prepare_context(encoder_hidden_states)
-        x = ops.nchw_to_nhwc(sample)
+        x = ops.pack_latents(ops.nchw_to_nhwc(sample), UNetEngine.CIN_PAD)
         t = _timesteps_f32(timestep, n, sample.device)
         down = mid = None
         if down_block_additional_residuals is not None:
             down = [ops.nchw_to_nhwc(r) for r in down_block_additional_residuals]
         if mid_block_additional_residual is not None:
             mid = ops.nchw_to_nhwc(mid_block_additional_residual)
-        eps = eng.forward(x, n, h, w, t, ctx_kv, lc, down, mid)  # fp32 NHWC
-        out = eps.permute(0, 3, 1, 2).contiguous().to(sample.dtype)
+        eps = eng.forward(x, n, h, w, t, ctx_kv, lc, down, mid)  # fp32 [n*h*w, 8], first out_channels valid
+        co = self.arch_cfg.out_channels
+        out = eps[:, :co].reshape(n, h, w, co).permute(0, 3, 1, 2).contiguous().to(sample.dtype)
         if not return_dict:
             return (out,)
         return UNet2DConditionOutput(sample=out)
@@ -336,7 +337,7 @@ class BEVControlNetModel(_B200Module):
         eng = self._get_engine(ControlNetEngine)
         b, n_cam, c, h, w = sample.shape
         cond = self.prepare_conditions(camera_param, bboxes_3d_data, encoder_hidden_states, controlnet_cond)
-        x = ops.nchw_to_nhwc(sample.reshape(b * n_cam, c, h, w))
+        x = ops.pack_latents(ops.nchw_to_nhwc(sample.reshape(b * n_cam, c, h, w)), ControlNetEngine.CIN_PAD)
         t = _timesteps_f32(timestep, b, sample.device)
         if t.numel() == b and n_cam > 1:
             t = t.repeat_interleave(n_cam)  # 'b ... -> (b repeat) ...' (:840-841)

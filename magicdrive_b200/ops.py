@@ -121,7 +121,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
     d.h_out, d.w_out = h_out, w_out
     d.bias = _ptr(bias)
     d.rowbias = _ptr(rowbias)
-    d.rowbias_ld = rowbias.stride(0) if rowbias is not None else 0
+    d.rowbias_ld = (rowbias.stride(0) if rowbias.shape[0] > 1 else 0) if rowbias is not None else 0  # 1 row = shared by all images
     d.residual, d.ldr = _ptr(residual), ldr
     d.out, d.ldo, d.out_is_f32, d.out_scale = _ptr(out), ldo, int(out_f32), float(out_scale)
     d.epi_mode = 1 if geglu else 0
@@ -285,10 +285,23 @@ def f32_to_bf16(x):
     return out
 
 
-def cfg_ddim_step(eps, latents, coef, cfg: bool, guidance: float):
+def cfg_ddim_step(eps, latents, coef, cfg: bool, guidance: float, c: int = 4):
+    """eps fp32 [(2|1)*pixels, ld>=c]; latents fp32 [pixels, c] updated in place."""
     global _launches
     _need_cuda(eps, latents, coef)
-    check(_lib.lib().mdb_cfg_ddim_step(_ptr(eps), int(cfg), float(guidance), _ptr(coef), _ptr(latents),
+    check(_lib.lib().mdb_cfg_ddim_step(_ptr(eps), eps.stride(0), c, int(cfg), float(guidance), _ptr(coef), _ptr(latents),
                                        latents.numel(), _stream()), "mdb_cfg_ddim_step")
     _launches += 1
     return latents
+
+
+def pack_latents(x, cpad: int = 64, repeat: int = 1):
+    """[pix, cin] fp32/bf16 -> bf16 [repeat*pix, cpad] zero-padded channels."""
+    global _launches
+    _need_cuda(x)
+    pix, cin = x.shape
+    out = torch.empty((repeat * pix, cpad), dtype=BF16, device=x.device)
+    check(_lib.lib().mdb_pack_latents(_ptr(x), int(x.dtype == F32), pix, cin, cpad, repeat, _ptr(out), _stream()),
+          "mdb_pack_latents")
+    _launches += 1
+    return out

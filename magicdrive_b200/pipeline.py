@@ -60,12 +60,12 @@ class BEVControlNetDenoiser:
         ue, ce = st["ue"], st["ce"]
         V, h, w = st["V"], st["h"], st["w"]
         lat = st["latents"]  # fp32 [S*ncam*h*w, 4] NHWC, S scenes (no CFG duplication)
-        x = ops.f32_to_bf16(lat)
-        if st["cfg"]:
-            x = torch.cat([x, x], 0)  # [uncond ; cond] share the latents (:352-354)
-        down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"])
-        eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid)  # fp32 [V, h, w, 4]
-        ops.cfg_ddim_step(eps.view(2 if st["cfg"] else 1, -1), lat, st["coef_dev"], st["cfg"], st["guidance"])
+        # bf16, channel-padded to one K block; CFG: [uncond ; cond] share the latents (:352-354) -> repeat = 2
+        x = ops.pack_latents(lat, ue.CIN_PAD, repeat=2 if st["cfg"] else 1)
+        down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
+                                     temb_all=st.get("c_temb"))
+        eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid, temb_all=st.get("u_temb"))
+        ops.cfg_ddim_step(eps, lat, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
 
     @torch.no_grad()
     def prepare(self, latents, prompt_embeds, negative_prompt_embeds, camera_param, bboxes_3d_data, image,
@@ -119,12 +119,22 @@ class BEVControlNetDenoiser:
     def _set_step(self, st, i):
         st["t_dev"].copy_(st["t_table"][i], non_blocking=True)
         st["coef_dev"].copy_(st["coef_table"][i], non_blocking=True)
+        st["u_temb"].copy_(st["u_temb_table"][i:i + 1], non_blocking=True)
+        st["c_temb"].copy_(st["c_temb_table"][i:i + 1], non_blocking=True)
 
     def set_schedule(self, st, num_inference_steps):
         ts = self.scheduler.set_timesteps(num_inference_steps)
         dev = st["latents"].device
         st["t_table"] = torch.tensor(ts, dtype=F32, device=dev)[:, None].expand(-1, st["V"]).contiguous()
         st["coef_table"] = torch.tensor(self.scheduler.coefs, dtype=F32, device=dev)
+        # the time-embedding MLP + all time_emb_proj layers depend only on t: one table for the whole schedule
+        # (every view-sample of a step shares t, so one row serves all images: rowbias stride 0)
+        tt = torch.tensor(ts, dtype=F32, device=dev)
+        st["u_temb_table"] = st["ue"].time_embed(tt)
+        st["c_temb_table"] = st["ce"].time_embed(tt)
+        if "u_temb" not in st or st["u_temb"].shape[1] != st["u_temb_table"].shape[1]:
+            st["u_temb"] = torch.zeros_like(st["u_temb_table"][:1])
+            st["c_temb"] = torch.zeros_like(st["c_temb_table"][:1])
         return ts
 
     def run_steps(self, st, first: int, last: int):

@@ -262,5 +262,13 @@ def test_cfg_ddim(cuda_lib):
     lat = torch.randn(n, device="cuda", generator=g)
     coef = torch.tensor([1.01, -0.05], device="cuda")
     ref = 1.01 * lat + (-0.05) * (eps[0] + 2.0 * (eps[1] - eps[0]))
-    out = ops.cfg_ddim_step(eps, lat.clone(), coef, True, 2.0)
-    torch.testing.assert_close(out, ref, atol=1e-6, rtol=1e-6)
+    # eps rows are [pixel, 8] with 4 valid channels (the padded conv_out output)
+    eps8 = torch.zeros(2 * (n // 4), 8, device="cuda")
+    eps8[:, :4] = eps.view(-1, 4)
+    out = ops.cfg_ddim_step(eps8, lat.clone().view(-1, 4), coef, True, 2.0, c=4)
+    torch.testing.assert_close(out.view(-1), ref, atol=1e-6, rtol=1e-6)
+    # latent packing: fp32 [pix, 4] -> bf16 [2*pix, 64]
+    x = torch.randn(100, 4, device="cuda", generator=g)
+    pk = ops.pack_latents(x, 64, repeat=2)
+    assert pk.shape == (200, 64) and torch.equal(pk[:100, :4], x.to(torch.bfloat16)) and torch.equal(pk[100:], pk[:100])
+    assert pk[:, 4:].abs().max().item() == 0
