@@ -9,8 +9,12 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include "../../include/magicdrive_b200.h"
+#define MDB_NEED_TENSORMAP
 #include "common_host.h"
+#include "attention_tc.cuh"
 
 namespace {
 
@@ -269,6 +273,47 @@ int launch_attention(const void* q, int ldq, const void* k, int ldk, const void*
   return MDB_OK;
 }
 
+// ---------------------------------------------------------------- tcgen05 path
+// [B, L, heads*D] (row stride ld) as a 4-D map (d, head, token, batch); box = (64, 1, 128, 1): the head dim is
+// zero-padded to 64-wide chunks by TMA out-of-bounds fill, rows beyond L are zero-filled too.
+bool make_qkv_map(CUtensorMap* m, const void* ptr, int d, int heads, int l, int b, int ld) {
+  mdb::EncodeTiledFn enc = mdb::get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)l, (cuuint64_t)b};
+  cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)ld * 2, (cuuint64_t)l * ld * 2};
+  cuuint32_t box[4] = {64u, 1u, (cuuint32_t)mdb::ATT_BM, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int D>
+int launch_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
+                        int heads, int lq, int lk, int b_kv, const int* kv_index, int n_sets, float scale, cudaStream_t st) {
+  using Cfg = mdb::AttnTcCfg<D>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mdb::attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  CUtensorMap tq, tk, tv;
+  if (!make_qkv_map(&tq, q, D, heads, lq, b, ldq) || !make_qkv_map(&tk, k, D, heads, lk, b_kv, ldk) ||
+      !make_qkv_map(&tv, v, D, heads, lk, b_kv, ldv))
+    return mdb::set_error(MDB_ERR_CUDA, "mdb_attention: cuTensorMapEncodeTiled failed (d=%d heads=%d lq=%d lk=%d)", D, heads,
+                          lq, lk);
+  mdb::AttnTcParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo, p.lq = lq, p.lk = lk, p.kv_index = kv_index, p.n_sets = n_sets;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
+  mdb::attention_tc_kernel<D><<<grid, 192, Cfg::kSmemBytes, st>>>(tq, tk, tv, p);
+  MDB_CHECK_LAUNCH("attention_tc_kernel");
+  return MDB_OK;
+}
+
 }  // namespace
 
 extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
@@ -280,6 +325,19 @@ extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, con
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return set_error(MDB_ERR_UNSUPPORTED, "mdb_attention: strides must be multiples of 8");
   if (lq <= 0 || lk <= 0 || b <= 0 || heads <= 0) return set_error(MDB_ERR_INVALID, "mdb_attention: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* legacy = getenv("MDB_ATTN_LEGACY");
+  if (!(legacy && legacy[0] == '1')) {
+    // tcgen05 path.  K/V batch count: the cross-view index addresses views of the same tensor as q.
+    const int b_kv = b;
+    switch (d) {
+      case 40: return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      case 80: return launch_attention_tc<80>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      case 160: return launch_attention_tc<160>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      case 32: return launch_attention_tc<32>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      case 64: return launch_attention_tc<64>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      default: break;
+    }
+  }
   switch (d) {
     case 40: return launch_attention<40>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, kv_index, n_sets, scale, st);
     case 80: return launch_attention<80>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, kv_index, n_sets, scale, st);

@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "../../include/magicdrive_b200.h"
+#define MDB_NEED_TENSORMAP
 #include "common_host.h"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
@@ -14,23 +15,6 @@
 using namespace mdb;
 
 namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
 
 // 4-D activation map: dims (C, W, H, N) innermost first; pixel stride = ld elements.
 bool make_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int n, int h, int w, int bn, int bh, int bw,

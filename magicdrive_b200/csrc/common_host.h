@@ -14,6 +14,31 @@ inline int set_error(int code, const char* fmt, ...) {
 }
 }  // namespace mdb
 
+#ifdef MDB_NEED_TENSORMAP
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+namespace mdb {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+inline EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+}  // namespace mdb
+#endif
+
 #define MDB_CHECK_LAUNCH(name)                                                                   \
   do {                                                                                           \
     cudaError_t e__ = cudaGetLastError();                                                        \

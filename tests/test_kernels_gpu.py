@@ -156,9 +156,11 @@ def test_layernorm(cuda_lib, c):
     assert _rel(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("legacy", [0, 1])  # 0 = tcgen05 kernel (default), 1 = mma.sync kernel
 @pytest.mark.parametrize("d,heads", [(40, 8), (80, 8), (160, 8), (32, 2), (64, 2)])
-@pytest.mark.parametrize("lq,lk", [(1400, 1400), (350, 98), (91, 91), (28, 28), (70, 130)])
-def test_attention(cuda_lib, d, heads, lq, lk):
+@pytest.mark.parametrize("lq,lk", [(1400, 1400), (350, 98), (91, 91), (28, 28), (70, 130), (130, 257)])
+def test_attention(cuda_lib, monkeypatch, d, heads, lq, lk, legacy):
+    monkeypatch.setenv("MDB_ATTN_LEGACY", str(legacy))
     g = torch.Generator(device="cuda").manual_seed(9)
     b = 3
     c = heads * d
@@ -176,10 +178,13 @@ def test_attention(cuda_lib, d, heads, lq, lk):
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=5e-3)
 
 
-def test_attention_two_sets_cross_view(cuda_lib):
+@pytest.mark.parametrize("legacy", [0, 1])
+@pytest.mark.parametrize("l,heads,d", [(350, 8, 80), (1400, 8, 40), (91, 8, 160)])
+def test_attention_two_sets_cross_view(cuda_lib, monkeypatch, legacy, l, heads, d):
     """attn4 'add' mode: out[view i] = attn(q_i, kv_left(i)) + attn(q_i, kv_right(i)) (blocks.py:112-121,213-217)."""
+    monkeypatch.setenv("MDB_ATTN_LEGACY", str(legacy))
     g = torch.Generator(device="cuda").manual_seed(10)
-    scenes, ncam, l, heads, d = 2, 6, 350, 8, 80
+    scenes, ncam = 2, 6
     c = heads * d
     b = scenes * ncam
     qkv = _bf(torch.randn(b * l, 3 * c, device="cuda", generator=g))
