@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
                                                      const __nv_bfloat16* __restrict__ x1, int c1, int ld1, int hw,
                                                      int groups, float eps, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, int silu,
-                                                     __nv_bfloat16* __restrict__ out, int ldo) {
+                                                     __nv_bfloat16* __restrict__ out, int ldo, uint32_t inv_pp) {
   __shared__ float red[T / 32];
   __shared__ float bcast;
   const int g = blockIdx.x, img = blockIdx.y;
@@ -134,8 +134,14 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
   const int units = hw * pp;
   const int cbase = g * cpg;
   const long long pix0 = static_cast<long long>(img) * hw;
+  // u / pp by multiply-high with a host-computed reciprocal (exact for u * pp < 2^32)
+  auto split = [&](int u, int& p, int& c) {
+    p = static_cast<int>(__umulhi(static_cast<uint32_t>(u), inv_pp));
+    c = cbase + 2 * (u - p * pp);
+  };
   auto src = [&](int u) -> const uint32_t* {
-    const int p = u / pp, c = cbase + 2 * (u - p * pp);
+    int p, c;
+    split(u, p, c);
     return (c < c0) ? reinterpret_cast<const uint32_t*>(x0 + (pix0 + p) * ld0 + c)
                     : reinterpret_cast<const uint32_t*>(x1 + (pix0 + p) * ld1 + (c - c0));
   };
@@ -154,16 +160,19 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
     __syncthreads();
     return bcast;
   };
+  // ---- load phase: every load is issued before the first use (memory-level parallelism = units per thread)
   uint32_t cache[GN_CACHE];
-  float s = 0.f;
+  const int nk = min(GN_CACHE, (units - static_cast<int>(threadIdx.x) + T - 1) / T);  // valid cached units of this thread
 #pragma unroll
   for (int k = 0; k < GN_CACHE; ++k) {
     const int u = threadIdx.x + k * T;
-    if (u < units) {
-      cache[k] = __ldg(src(u));
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
-      s += f.x + f.y;
-    }
+    cache[k] = (k < nk) ? __ldg(src(min(u, units - 1))) : 0u;  // bf16 zeros when out of range
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
+    s += f.x + f.y;
   }
   for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) {
     const uint32_t w = __ldg(src(u));
@@ -175,11 +184,9 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
   float sq = 0.f;
 #pragma unroll
   for (int k = 0; k < GN_CACHE; ++k) {
-    const int u = threadIdx.x + k * T;
-    if (u < units) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
-      sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-    }
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
+    const float d0 = f.x - mean, d1 = f.y - mean;
+    sq += (k < nk) ? (d0 * d0 + d1 * d1) : 0.f;
   }
   for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) {
     const uint32_t w = __ldg(src(u));
@@ -188,10 +195,13 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
   }
   const float rstd = rsqrtf(block_sum(sq) * inv_cnt + eps);
   auto emit = [&](int u, uint32_t w) {
-    const int p = u / pp, c = cbase + 2 * (u - p * pp);
+    int p, c;
+    split(u, p, c);
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-    float y0 = (f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-    float y1 = (f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c));
+    const float2 be = __ldg(reinterpret_cast<const float2*>(beta + c));
+    float y0 = (f.x - mean) * rstd * ga.x + be.x;
+    float y1 = (f.y - mean) * rstd * ga.y + be.y;
     if (silu) {
       y0 = y0 / (1.0f + __expf(-y0));
       y1 = y1 / (1.0f + __expf(-y1));
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
 #pragma unroll
   for (int k = 0; k < GN_CACHE; ++k) {
     const int u = threadIdx.x + k * T;
-    if (u < units) emit(u, cache[k]);
+    if (k < nk) emit(u, cache[k]);
   }
   for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) emit(u, __ldg(src(u)));
 }
@@ -278,15 +288,18 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
   if (c1 > 0 && !x1) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: c1>0 but x1 null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (((ctot / groups) & 1) == 0 && (c0 & 1) == 0 && !getenv("MDB_GN_TWO_KERNEL")) {
-    const long long units = static_cast<long long>(hw) * (ctot / groups / 2);
+    const int pp = ctot / groups / 2;
+    const long long units = static_cast<long long>(hw) * pp;
+    const uint32_t inv_pp = static_cast<uint32_t>((0x100000000ULL + pp - 1) / pp);  // ceil(2^32 / pp)
+    if (units * pp >= 0xffffffffLL) return set_error(MDB_ERR_UNSUPPORTED, "mdb_groupnorm: tensor too large");
     if (units <= 256LL * GN_CACHE)
       gn_fused_kernel<256><<<dim3(groups, n_img), 256, 0, st>>>(
           static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
-          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo);
+          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo, inv_pp);
     else
-      gn_fused_kernel<1024><<<dim3(groups, n_img), 1024, 0, st>>>(
+      gn_fused_kernel<512><<<dim3(groups, n_img), 512, 0, st>>>(
           static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
-          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo);
+          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo, inv_pp);
     MDB_CHECK_LAUNCH("gn_fused_kernel");
     return MDB_OK;
   }

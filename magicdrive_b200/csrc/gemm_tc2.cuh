@@ -292,16 +292,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         const int ocol = on0 + c + cu * 4;
         if (ocol < out_n) {
+          // all residual loads first (independent, 8 in flight per lane), then add + store
+          uint2 r2[8];
+          const bool has_res = (p.residual != nullptr) && !geglu;
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              r2[i] = (cpix[i] >= 0) ? __ldg(reinterpret_cast<const uint2*>(p.residual + cpix[i] * p.ldr + ocol))
+                                     : make_uint2(0u, 0u);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + crow_sub;
             const long long px = cpix[i];
             if (px < 0) continue;
             float4 a = reinterpret_cast<const float4*>(stg + rr * 32)[cu ^ (rr & 7)];
-            if (p.residual && !geglu) {
-              const uint2 r2 = __ldg(reinterpret_cast<const uint2*>(p.residual + px * p.ldr + ocol));
-              const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r2.x));
-              const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r2.y));
+            if (has_res) {
+              const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r2[i].x));
+              const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r2[i].y));
               a.x += r01.x, a.y += r01.y, a.z += r23.x, a.w += r23.y;
             }
             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + px * p.ldo + ocol) =
