@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
   const long long pix0 = static_cast<long long>(img) * hw;
   // u / pp by multiply-high with a host-computed reciprocal (exact for u * pp < 2^32)
   auto split = [&](int u, int& p, int& c) {
-    p = static_cast<int>(__umulhi(static_cast<uint32_t>(u), inv_pp));
+    p = (pp == 1) ? u : static_cast<int>(__umulhi(static_cast<uint32_t>(u), inv_pp));
     c = cbase + 2 * (u - p * pp);
   };
   auto src = [&](int u) -> const uint32_t* {

@@ -44,6 +44,7 @@ struct GemmParams {
   int ldo;
   float out_scale;
   float* partial;  // [splits][pixels][n_out] fp32 workspace (EPI_PARTIAL_F32)
+  long long* trace;  // optional debug: per-CTA clock64 stamps (16 slots per CTA, first 8 CTAs)
 };
 
 constexpr int kBlockM = 128;

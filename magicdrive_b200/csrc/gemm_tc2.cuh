@@ -23,8 +23,7 @@ struct GemmCfg2 {
   static constexpr int kStages = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 160) ? 5 : 6);
   static constexpr int kAccStride = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128) ? 128 : 256;  // TMEM columns per stage
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kStageOutBytes = 4 * 32 * 32 * 4;  // per epilogue warp: [32 rows][32 cols] fp32, XOR-swizzled
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static constexpr int kThreads = 192;
 };
 
@@ -39,8 +38,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * kABytes;
-  float* sm_out = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);  // 4 x 4 KiB epilogue staging
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + Cfg::kStageOutBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
@@ -48,6 +46,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* trace = (p.trace != nullptr && blockIdx.x < 8) ? p.trace + blockIdx.x * 16 : nullptr;
+#define MDB_TRACE(slot) do { if (trace) trace[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) MDB_TRACE(0);
   const int cb_total = p.cblocks0 + p.cblocks1;
   const int kb_total = p.taps_h * p.taps_w * cb_total;
   const int total_tiles = pp.m_tiles * pp.n_tiles * pp.splits;
@@ -76,6 +77,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) MDB_TRACE(1);
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -83,6 +85,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t tx_bytes = static_cast<uint32_t>(p.bn * p.bh * p.bw) * (kBlockK * 2) + Cfg::kBBytes;
       int stage = 0;
       uint32_t phase = 0;
+      MDB_TRACE(2);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int mt = t % pp.m_tiles;
         const int rest = t / pp.m_tiles;
@@ -114,6 +117,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           }
         }
       }
+      MDB_TRACE(3);
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -133,6 +137,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (lane == 0 && it == 0 && i == 0) MDB_TRACE(4);
         if (elect_one()) {
           const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smA + stage * kABytes));
           const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smB + stage * Cfg::kBBytes));
@@ -148,20 +153,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           phase ^= 1;
         }
       }
+      if (lane == 0 && it == 0) MDB_TRACE(5);
     }
+    if (lane == 0) MDB_TRACE(6);
   } else {
     // =========================== epilogue (warps 2..5) ===========================
-    // Row phase: thread = one accumulator row (TMEM lane): tcgen05.ld 32 columns, + bias + per-image shift, scale (fp32).
-    // The 32x32 fp32 block is then transposed through a swizzled smem tile so that the residual loads and the output
-    // stores are coalesced (8 lanes cover 32 consecutive columns of one row, 4 rows per instruction) instead of 32
-    // lanes touching 32 different rows.
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int box_hw = p.bh * p.bw;
+    const int li = row / box_hw;
+    const int rem = row - li * box_hw;
+    const int lh = rem / p.bw;
+    const int lw = rem - lh * p.bw;
     const long long pixels_total = static_cast<long long>(p.n_img) * p.h_out * p.w_out;
-    float* stg = sm_out + q * (32 * 32);
-    const int crow_sub = lane >> 3;  // coalesced phase: row within a group of 4
-    const int cu = lane & 7;         // 16-byte (4 fp32) unit within the 32-column block
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int mt = t % pp.m_tiles;
@@ -171,77 +175,68 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
-      auto pixel_of = [&](int r, int& img_out) -> long long {
-        const int li = r / box_hw;
-        const int rem = r - li * box_hw;
-        const int lh = rem / p.bw;
-        const int lw = rem - lh * p.bw;
-        const int img = tn * p.bn + li, oh = th * p.bh + lh, ow = tw * p.bw + lw;
-        img_out = img;
-        const bool ok = (li < p.bn) && (img < p.n_img) && (oh < p.h_out) && (ow < p.w_out);
-        return ok ? (static_cast<long long>(img) * p.h_out + oh) * p.w_out + ow : -1;
-      };
-      int img;
-      const long long pix = pixel_of(row, img);
-      const bool row_ok = pix >= 0;
-      // pixels of the 8 rows this lane serves in the coalesced phase
-      long long cpix[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int dummy;
-        cpix[i] = pixel_of(q * 32 + i * 4 + crow_sub, dummy);
-      }
+      const int img = tn * p.bn + li, oh = th * p.bh + lh, ow = tw * p.bw + lw;
       const int n0 = nt * BLOCK_N;
+      const bool row_ok = (li < p.bn) && (img < p.n_img) && (oh < p.h_out) && (ow < p.w_out);
+      const long long pix = (static_cast<long long>(img) * p.h_out + oh) * p.w_out + ow;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && it == 0) MDB_TRACE(7);
       const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      const bool geglu = (p.epi_mode == EPI_GEGLU);
-      const bool staged = geglu || (p.epi_mode == EPI_LINEAR && !p.out_is_f32);
-      constexpr int HALF = BLOCK_N / 2;
-      const int n_chunks = geglu ? HALF / 32 : BLOCK_N / 32;
-      const int out_n = geglu ? p.n_out / 2 : p.n_out;        // valid output columns
-      const int on0 = geglu ? nt * HALF : n0;                 // first output column of this tile
 
+      if (p.epi_mode == EPI_GEGLU) {
+        constexpr int HALF = BLOCK_N / 2;
+        const int on0 = nt * HALF;
+        const int n_half = p.n_out / 2;
 #pragma unroll 1
-      for (int ci = 0; ci < n_chunks; ++ci) {
-        const int c = ci * 32;
-        __syncwarp();
-        float f[32];
-        if (geglu) {
-          uint32_t v[32], g[32];
-          tmem_ld_32x32(lane_addr + c, v);
-          tmem_ld_32x32(lane_addr + HALF + c, g);
+        for (int c = 0; c < HALF; c += 16) {
+          __syncwarp();
+          uint32_t v[16], g[16];
+          tmem_ld_32x16(lane_addr + c, v);
+          tmem_ld_32x16(lane_addr + HALF + c, g);
           tmem_ld_wait();
+          if (row_ok && on0 + c < n_half) {
+            uint32_t o[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]), gg = __uint_as_float(g[j]);
-            if (p.bias) {
-              a += __ldg(p.bias + n0 + c + j);
-              gg += __ldg(p.bias + n0 + HALF + c + j);
+            for (int j = 0; j < 16; j += 2) {
+              float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+              float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
+              if (p.bias) {
+                a0 += __ldg(p.bias + n0 + c + j);
+                a1 += __ldg(p.bias + n0 + c + j + 1);
+                g0 += __ldg(p.bias + n0 + HALF + c + j);
+                g1 += __ldg(p.bias + n0 + HALF + c + j + 1);
+              }
+              o[j >> 1] = pack_bf16(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
             }
-            f[j] = a * gelu_erf(gg);
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + on0 + c);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
-        } else {
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          __syncwarp();
           uint32_t v[32];
           tmem_ld_32x32(lane_addr + c, v);
           tmem_ld_wait();
           const int col0 = n0 + c;
-          if (col0 >= p.n_out) continue;  // warp-uniform
+          if (!row_ok || col0 >= p.n_out) continue;
           if (p.epi_mode == EPI_PARTIAL_F32) {
-            if (row_ok) {
-              float* dst = p.partial + (static_cast<long long>(z) * pixels_total + pix) * p.n_out + col0;
+            float* dst = p.partial + (static_cast<long long>(z) * pixels_total + pix) * p.n_out + col0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (col0 + j < p.n_out)
-                  *reinterpret_cast<float4*>(dst + j) =
-                      make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                  __uint_as_float(v[j + 3]));
-              }
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < p.n_out)
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3]));
             }
             continue;
           }
+          float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
@@ -253,7 +248,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
             }
           }
-          if (p.rowbias && row_ok) {
+          if (p.rowbias) {
             const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -267,53 +262,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
           }
-          if (!staged) {  // fp32 output: direct row-wise stores (+ residual)
-            if (row_ok) {
-              if (p.residual) {
-                const __nv_bfloat16* rs = p.residual + pix * p.ldr + col0;
+          if (p.residual) {
+            const __nv_bfloat16* rs = p.residual + pix * p.ldr + col0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.n_out) f[j] += __bfloat162float(rs[j]);
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.n_out) {
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rs + j));
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) {
+                  const float2 rf = __bfloat1622float2(rh[tt]);
+                  f[j + 2 * tt] += rf.x;
+                  f[j + 2 * tt + 1] += rf.y;
+                }
               }
-              float* dst = static_cast<float*>(p.out) + pix * p.ldo + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (col0 + j < p.n_out) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             }
-            continue;
           }
-        }
-        // ---- staged, coalesced bf16 store of the 32x32 block (output columns on0 + c ...)
-        {
-          float4* srow = reinterpret_cast<float4*>(stg + lane * 32);
+          if (p.out_is_f32) {
+            float* dst = static_cast<float*>(p.out) + pix * p.ldo + col0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) srow[u ^ (lane & 7)] = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
-        }
-        __syncwarp();
-        const int ocol = on0 + c + cu * 4;
-        if (ocol < out_n) {
-          // all residual loads first (independent, 8 in flight per lane), then add + store
-          uint2 r2[8];
-          const bool has_res = (p.residual != nullptr) && !geglu;
-          if (has_res) {
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < p.n_out) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              r2[i] = (cpix[i] >= 0) ? __ldg(reinterpret_cast<const uint2*>(p.residual + cpix[i] * p.ldr + ocol))
-                                     : make_uint2(0u, 0u);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + crow_sub;
-            const long long px = cpix[i];
-            if (px < 0) continue;
-            float4 a = reinterpret_cast<const float4*>(stg + rr * 32)[cu ^ (rr & 7)];
-            if (has_res) {
-              const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r2[i].x));
-              const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r2[i].y));
-              a.x += r01.x, a.y += r01.y, a.z += r23.x, a.w += r23.y;
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.n_out)
+                *reinterpret_cast<uint4*>(dst + j) =
+                    make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]), pack_bf16(f[j + 4], f[j + 5]),
+                               pack_bf16(f[j + 6], f[j + 7]));
             }
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + px * p.ldo + ocol) =
-                make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
           }
         }
       }
@@ -321,10 +299,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (warp == 2 && lane == 0 && it == 0) MDB_TRACE(8);
+    }
+    if (warp == 2 && lane == 0) {
+      MDB_TRACE(9);
+      if (trace) trace[11] = it;
     }
   }
 
   __syncthreads();
+  if (threadIdx.x == 0) MDB_TRACE(10);
+#undef MDB_TRACE
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

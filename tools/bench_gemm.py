@@ -40,6 +40,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--trace", action="store_true", help="print per-CTA clock64 phase stamps of the persistent kernel")
 ap.add_argument("--profile", action="store_true", help="one launch per shape between cudaProfilerStart/Stop (for ncu)")
 args = ap.parse_args()
 dev = "cuda"
@@ -61,6 +62,18 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
     for _ in range(3):
         ops.gemm_conv(x, wt, **kw)
     torch.cuda.synchronize()
+    if args.trace:
+        tr = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
+        flush.zero_()
+        ops.gemm_conv(x, wt, trace=tr, **kw)
+        torch.cuda.synchronize()
+        tr = tr.view(8, 16).cpu()
+        names = ["entry", "prologue_done", "tma_first", "tma_last", "mma_first_full", "mma_tile0_done", "mma_all_done",
+                 "epi_tile0_ready", "epi_tile0_done", "epi_all_done", "exit"]
+        print(f"{name}: per-CTA cycles since entry (CTA 0, 1, 7); tiles/CTA = {tr[0, 11].item()}")
+        for cta in (0, 1, 7):
+            print("   ", " ".join(f"{n}={int(tr[cta, i] - tr[cta, 0])}" for i, n in enumerate(names)))
+        continue
     if args.profile:
         torch.cuda.profiler.start()
         ops.gemm_conv(x, wt, **kw)
