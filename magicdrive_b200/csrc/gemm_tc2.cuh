@@ -193,22 +193,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll 1
         for (int c = 0; c < HALF; c += 16) {
           __syncwarp();
+          if (on0 + c >= n_half) break;  // warp-uniform
+          // bias first (independent loads in flight while the TMEM load completes)
+          float4 bv[4], bg[4];
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + 4 * j));
+              bg[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + HALF + c + 4 * j));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = bg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           uint32_t v[16], g[16];
           tmem_ld_32x16(lane_addr + c, v);
           tmem_ld_32x16(lane_addr + HALF + c, g);
           tmem_ld_wait();
-          if (row_ok && on0 + c < n_half) {
+          if (row_ok) {
+            const float* bvf = reinterpret_cast<const float*>(bv);
+            const float* bgf = reinterpret_cast<const float*>(bg);
             uint32_t o[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
-              float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
-              if (p.bias) {
-                a0 += __ldg(p.bias + n0 + c + j);
-                a1 += __ldg(p.bias + n0 + c + j + 1);
-                g0 += __ldg(p.bias + n0 + HALF + c + j);
-                g1 += __ldg(p.bias + n0 + HALF + c + j + 1);
-              }
+              const float a0 = __uint_as_float(v[j]) + bvf[j], a1 = __uint_as_float(v[j + 1]) + bvf[j + 1];
+              const float g0 = __uint_as_float(g[j]) + bgf[j], g1 = __uint_as_float(g[j + 1]) + bgf[j + 1];
               o[j >> 1] = pack_bf16(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
             }
             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + on0 + c);
@@ -220,77 +229,89 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
           __syncwarp();
-          uint32_t v[32];
-          tmem_ld_32x32(lane_addr + c, v);
-          tmem_ld_wait();
           const int col0 = n0 + c;
-          if (!row_ok || col0 >= p.n_out) continue;
+          if (col0 >= p.n_out) break;  // warp-uniform: nothing left in this tile
+          const bool full = (col0 + 32 <= p.n_out);
           if (p.epi_mode == EPI_PARTIAL_F32) {
-            float* dst = p.partial + (static_cast<long long>(z) * pixels_total + pix) * p.n_out + col0;
+            uint32_t v[32];
+            tmem_ld_32x32(lane_addr + c, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float* dst = p.partial + (static_cast<long long>(z) * pixels_total + pix) * p.n_out + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.n_out)
-                *reinterpret_cast<float4*>(dst + j) =
-                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                __uint_as_float(v[j + 3]));
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.n_out)
+                  *reinterpret_cast<float4*>(dst + j) =
+                      make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                  __uint_as_float(v[j + 3]));
+              }
             }
             continue;
           }
-          float f[32];
+          // ---- 1. issue every global load of this chunk before anything consumes one (the old per-column guards
+          //         serialised ~20 load latencies per chunk: 18k cycles per tile on the K=320 GEMMs)
+          float4 bv[8], rv[8];
+          uint4 res[4];
+          const int ncol4 = full ? 8 : (p.n_out - col0) / 4;  // valid float4 groups (n_out % 8 == 0)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.n_out) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            const int jj = (j < ncol4) ? j : 0;  // clamp: always a valid address, never stored when out of range
+            bv[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (p.rowbias) {
+          const bool use_rb = (p.rowbias != nullptr) && row_ok;
+          if (use_rb) {
             const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.n_out) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(rb + j));
-                f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
-              }
-            }
+            for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(rb + 4 * ((j < ncol4) ? j : 0)));
+          }
+          const bool use_res = (p.residual != nullptr) && row_ok;
+          if (use_res) {
+            const __nv_bfloat16* rs = p.residual + pix * p.ldr + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(rs + 8 * ((2 * j < ncol4) ? j : 0)));
+          }
+          // ---- 2. accumulator
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + c, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          // ---- 3. math
+          float f[32];
+          const float* bvf = reinterpret_cast<const float*>(bv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bvf[j];
+          if (use_rb) {
+            const float* rvf = reinterpret_cast<const float*>(rv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += rvf[j];
           }
           if (p.out_scale != 1.0f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
           }
-          if (p.residual) {
-            const __nv_bfloat16* rs = p.residual + pix * p.ldr + col0;
+          if (use_res) {
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(res);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.n_out) {
-                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rs + j));
-                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-                for (int tt = 0; tt < 4; ++tt) {
-                  const float2 rf = __bfloat1622float2(rh[tt]);
-                  f[j + 2 * tt] += rf.x;
-                  f[j + 2 * tt + 1] += rf.y;
-                }
-              }
+            for (int j = 0; j < 16; ++j) {
+              const float2 rf = __bfloat1622float2(rh[j]);
+              f[2 * j] += rf.x;
+              f[2 * j + 1] += rf.y;
             }
           }
+          // ---- 4. store
           if (p.out_is_f32) {
             float* dst = static_cast<float*>(p.out) + pix * p.ldo + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (col0 + j < p.n_out) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            for (int j = 0; j < 8; ++j)
+              if (j < ncol4) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
             __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.n_out)
-                *reinterpret_cast<uint4*>(dst + j) =
-                    make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]), pack_bf16(f[j + 4], f[j + 5]),
-                               pack_bf16(f[j + 6], f[j + 7]));
+            for (int j = 0; j < 4; ++j) {
+              if (2 * j < ncol4)
+                *reinterpret_cast<uint4*>(dst + 8 * j) =
+                    make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
             }
           }
         }
