@@ -68,6 +68,7 @@ typedef struct {
   int force_block_n;    /* 0 = auto; test hook */
   int force_splits;     /* 0 = auto; test hook */
   int kernel_variant;   /* 0 = persistent double-buffered kernel (default); 1 = one-tile-per-CTA kernel; test hook */
+  int debug_flags;      /* ablation hook (0 in production): 1 skip stores, 2 skip epilogue loads, 4 skip TMEM loads */
   void* trace;          /* debug: device int64[8*16] receiving per-CTA clock64 stamps of the persistent kernel, or NULL */
 } mdb_gemm_desc;
 

@@ -27,7 +27,7 @@ class GemmDesc(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int), ("out_is_f32", C.c_int), ("out_scale", C.c_float),
         ("epi_mode", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-        ("force_block_n", C.c_int), ("force_splits", C.c_int), ("kernel_variant", C.c_int), ("trace", C.c_void_p),
+        ("force_block_n", C.c_int), ("force_splits", C.c_int), ("kernel_variant", C.c_int), ("debug_flags", C.c_int), ("trace", C.c_void_p),
     ]
 
 

@@ -235,6 +235,7 @@ extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
   gp.out = d->out, gp.ldo = d->ldo, gp.out_scale = d->out_scale;
   gp.partial = static_cast<float*>(d->workspace);
   gp.trace = static_cast<long long*>(d->trace);
+  gp.debug_flags = d->debug_flags;
 
   if (d->kernel_variant != 1) {
     switch (pl.block_n) {

@@ -44,6 +44,7 @@ struct GemmParams {
   int ldo;
   float out_scale;
   float* partial;  // [splits][pixels][n_out] fp32 workspace (EPI_PARTIAL_F32)
+  int debug_flags;   // debug/ablation: 1 = skip output stores, 2 = skip bias/shift/residual loads, 4 = skip TMEM loads
   long long* trace;  // optional debug: per-CTA clock64 stamps (16 slots per CTA, first 8 CTAs)
 };
 

@@ -95,7 +95,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
               residual: Optional[torch.Tensor] = None, ldr: int = 0, out: Optional[torch.Tensor] = None,
               ldo: Optional[int] = None, out_f32: bool = False, out_scale: float = 1.0, geglu: bool = False,
               force_block_n: int = 0, force_splits: int = 0, allow_split_k: bool = True,
-              kernel_variant: int = 0, trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+              kernel_variant: int = 0, trace: Optional[torch.Tensor] = None, debug_flags: int = 0) -> torch.Tensor:
     """tcgen05 GEMM / implicit-GEMM conv (mdb_gemm_conv).  `a0` (and `a1`) are NHWC bf16 buffers whose pixel
     stride is lda* elements; `w` is bf16 [n_out, taps*taps*(c0+c1)]."""
     global _launches
@@ -133,6 +133,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
     d.force_block_n, d.force_splits = force_block_n, force_splits
     d.kernel_variant = kernel_variant or GEMM_VARIANT
     d.trace = _ptr(trace)
+    d.debug_flags = debug_flags
     L = _lib.lib()
     e0 = _prof_begin()
     check(L.mdb_gemm_conv(C.byref(d), _stream()), "mdb_gemm_conv")

@@ -40,6 +40,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--debug-flags", type=int, default=0)
 ap.add_argument("--trace", action="store_true", help="print per-CTA clock64 phase stamps of the persistent kernel")
 ap.add_argument("--profile", action="store_true", help="one launch per shape between cudaProfilerStart/Stop (for ncu)")
 args = ap.parse_args()
@@ -58,7 +59,7 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
         wt, b = pack_geglu(wt, b)
     r = torch.randn(pix, co, device=dev, generator=g).bfloat16() if res else None
     kw = dict(n_img=n, h_in=h, w_in=w, c0=ci, lda0=ci, n_out=co, taps=taps, pad=taps // 2, bias=b, residual=r,
-              ldr=co if res else 0, geglu=geglu, kernel_variant=args.variant)
+              ldr=co if res else 0, geglu=geglu, kernel_variant=args.variant, debug_flags=args.debug_flags)
     for _ in range(3):
         ops.gemm_conv(x, wt, **kw)
     torch.cuda.synchronize()
@@ -72,7 +73,8 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
                  "epi_tile0_ready", "epi_tile0_done", "epi_all_done", "exit"]
         print(f"{name}: per-CTA cycles since entry (CTA 0, 1, 7); tiles/CTA = {tr[0, 11].item()}")
         for cta in (0, 1, 7):
-            print("   ", " ".join(f"{n}={int(tr[cta, i] - tr[cta, 0])}" for i, n in enumerate(names)))
+            print("   ", " ".join(f"{n}={int(tr[cta, i] - tr[cta, 0])}" for i, n in enumerate(names)),
+                  "chunk_starts=" + ",".join(str(int(tr[cta, 12 + i] - tr[cta, 0])) for i in range(3)))
         continue
     if args.profile:
         torch.cuda.profiler.start()
