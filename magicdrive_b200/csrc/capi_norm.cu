@@ -116,15 +116,24 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, in
 }
 
 // ---- GroupNorm, single kernel: one CTA per (image, group).  The group's hw x cpg slab (a few tens of KB, L2-resident:
-// it was just written by the producing GEMM) is read once into registers, mean and variance are computed exactly
-// (two-pass over the register copy), then normalise + affine (+SiLU) and store.  No atomics, no memset, no stats buffer.
-constexpr int GN_CACHE = 56;  // bf16x2 units cached per thread
-template <int T>
-__global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0,
-                                                     const __nv_bfloat16* __restrict__ x1, int c1, int ld1, int hw,
-                                                     int groups, float eps, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, int silu,
-                                                     __nv_bfloat16* __restrict__ out, int ldo, uint32_t inv_pp) {
+// it was just written by the producing GEMM) is copied once into shared memory with 4-byte cp.async (every load in
+// flight at once, no registers, no unrolling: the first version cached the slab in 56 unrolled registers and spent
+// most of its time in instruction-cache misses), mean and variance are computed exactly (two passes over smem),
+// then normalise + affine (+SiLU) and store.  No atomics, no memset, no stats buffer.
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))),
+               "l"(src)
+               : "memory");
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0,
+                                                       const __nv_bfloat16* __restrict__ x1, int c1, int ld1, int hw,
+                                                       int groups, float eps, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int silu,
+                                                       __nv_bfloat16* __restrict__ out, int ldo, uint32_t inv_pp) {
+  constexpr int T = 256;
+  extern __shared__ uint32_t slab[];  // [units] bf16x2 (CACHED only)
   __shared__ float red[T / 32];
   __shared__ float bcast;
   const int g = blockIdx.x, img = blockIdx.y;
@@ -145,6 +154,10 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
     return (c < c0) ? reinterpret_cast<const uint32_t*>(x0 + (pix0 + p) * ld0 + c)
                     : reinterpret_cast<const uint32_t*>(x1 + (pix0 + p) * ld1 + (c - c0));
   };
+  auto value = [&](int u) -> float2 {
+    const uint32_t w = CACHED ? slab[u] : __ldg(src(u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+  };
   auto block_sum = [&](float v) -> float {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -160,44 +173,33 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
     __syncthreads();
     return bcast;
   };
-  // ---- load phase: every load is issued before the first use (memory-level parallelism = units per thread)
-  uint32_t cache[GN_CACHE];
-  const int nk = min(GN_CACHE, (units - static_cast<int>(threadIdx.x) + T - 1) / T);  // valid cached units of this thread
-#pragma unroll
-  for (int k = 0; k < GN_CACHE; ++k) {
-    const int u = threadIdx.x + k * T;
-    cache[k] = (k < nk) ? __ldg(src(min(u, units - 1))) : 0u;  // bf16 zeros when out of range
+  if (CACHED) {
+    for (int u = threadIdx.x; u < units; u += T) cp_async4(&slab[u], src(u));
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
   float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < GN_CACHE; ++k) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
-    s += f.x + f.y;
-  }
-  for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) {
-    const uint32_t w = __ldg(src(u));
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+#pragma unroll 4
+  for (int u = threadIdx.x; u < units; u += T) {
+    const float2 f = value(u);
     s += f.x + f.y;
   }
   const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
   const float mean = block_sum(s) * inv_cnt;
   float sq = 0.f;
-#pragma unroll
-  for (int k = 0; k < GN_CACHE; ++k) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cache[k]));
+#pragma unroll 4
+  for (int u = threadIdx.x; u < units; u += T) {
+    const float2 f = value(u);
     const float d0 = f.x - mean, d1 = f.y - mean;
-    sq += (k < nk) ? (d0 * d0 + d1 * d1) : 0.f;
-  }
-  for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) {
-    const uint32_t w = __ldg(src(u));
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-    sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+    sq += d0 * d0 + d1 * d1;
   }
   const float rstd = rsqrtf(block_sum(sq) * inv_cnt + eps);
-  auto emit = [&](int u, uint32_t w) {
+#pragma unroll 4
+  for (int u = threadIdx.x; u < units; u += T) {
     int p, c;
     split(u, p, c);
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+    const float2 f = value(u);
     const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c));
     const float2 be = __ldg(reinterpret_cast<const float2*>(beta + c));
     float y0 = (f.x - mean) * rstd * ga.x + be.x;
@@ -208,13 +210,7 @@ __global__ void __launch_bounds__(T) gn_fused_kernel(const __nv_bfloat16* __rest
     }
     __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
     *reinterpret_cast<uint32_t*>(out + (pix0 + p) * ldo + c) = *reinterpret_cast<uint32_t*>(&h);
-  };
-#pragma unroll
-  for (int k = 0; k < GN_CACHE; ++k) {
-    const int u = threadIdx.x + k * T;
-    if (k < nk) emit(u, cache[k]);
   }
-  for (int u = threadIdx.x + GN_CACHE * T; u < units; u += T) emit(u, __ldg(src(u)));
 }
 
 // ---- LayerNorm: one warp per row, values kept in registers (two-pass mean / variance like ATen).
@@ -292,14 +288,21 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
     const long long units = static_cast<long long>(hw) * pp;
     const uint32_t inv_pp = static_cast<uint32_t>((0x100000000ULL + pp - 1) / pp);  // ceil(2^32 / pp)
     if (units * pp >= 0xffffffffLL) return set_error(MDB_ERR_UNSUPPORTED, "mdb_groupnorm: tensor too large");
-    if (units <= 256LL * GN_CACHE)
-      gn_fused_kernel<256><<<dim3(groups, n_img), 256, 0, st>>>(
+    const size_t slab_bytes = static_cast<size_t>(units) * 4;
+    if (slab_bytes <= 96 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+      }
+      gn_fused_kernel<true><<<dim3(groups, n_img), 256, slab_bytes, st>>>(
           static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
           gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo, inv_pp);
-    else
-      gn_fused_kernel<512><<<dim3(groups, n_img), 512, 0, st>>>(
+    } else {
+      gn_fused_kernel<false><<<dim3(groups, n_img), 256, 0, st>>>(
           static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
           gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo, inv_pp);
+    }
     MDB_CHECK_LAUNCH("gn_fused_kernel");
     return MDB_OK;
   }
