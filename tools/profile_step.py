@@ -21,6 +21,7 @@ from magicdrive_b200.synthetic import synthetic_inputs  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cam")
 ap.add_argument("--scenes", type=int, default=1)
+ap.add_argument("--shape-log", default=None, help="write the ordered list of tensor-core launches (kind, shape) of the profiled step")
 ap.add_argument("--events", default=None, help="write a per-launch CUDA-event table of the tensor-core kernels here")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -55,8 +56,16 @@ if args.events:
             f.write(f"{sec * 1e6:9.1f} {100 * sec / tot:5.1f}% {n:4d} {sec * 1e6 / n:9.1f} {fl / sec / 1e12:8.1f}  {kind}  {info}\n")
     print("wrote", args.events)
 else:
+    from magicdrive_b200 import ops
+    if args.shape_log:
+        ops.start_profile()
     torch.cuda.profiler.start()
     pipe.run_steps(st, 2, 3)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+    if args.shape_log:
+        rec = ops.stop_profile(with_info=True)
+        with open(args.shape_log, "w") as f:
+            for kind, fl, sec, info in rec:
+                f.write(f"{kind}\t{fl:.0f}\t{info}\n")
     print("profiled one step")
