@@ -185,8 +185,9 @@ int launch2(const Plan& pl, const CUtensorMap& tA0, const CUtensorMap& tA1, cons
   const long long total = (long long)pp.m_tiles * pp.n_tiles * pp.splits;
   const int sms = num_sms();
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tc2_kernel<BN><<<grid, GemmCfg2<BN>::kThreads, GemmCfg2<BN>::kSmemBytes, st>>>(tA0, tA1, tB, pp);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(gemm_tc2_kernel<BN>, dim3(grid), dim3(GemmCfg2<BN>::kThreads), GemmCfg2<BN>::kSmemBytes, st, tA0,
+                             tA1, tB, pp);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "gemm_tc2_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
   return MDB_OK;
 }
@@ -259,11 +260,11 @@ extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
     const long long total4 = pixels * d->n_out / 4;
     const int threads = 256;
     const int blocks = (int)((total4 + threads - 1) / threads);
-    splitk_finalize_kernel<<<blocks, threads, 0, st>>>(
-        static_cast<const float*>(d->workspace), pl.splits, pixels, d->n_out, d->h_out * d->w_out, d->bias, d->rowbias,
-        d->rowbias_ld, static_cast<const __nv_bfloat16*>(d->residual), d->ldr, d->out, d->ldo, d->out_is_f32,
-        d->out_scale);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(splitk_finalize_kernel, dim3(blocks), dim3(threads), 0, st,
+                               static_cast<const float*>(d->workspace), pl.splits, pixels, d->n_out, d->h_out * d->w_out,
+                               d->bias, d->rowbias, d->rowbias_ld, static_cast<const __nv_bfloat16*>(d->residual), d->ldr,
+                               d->out, d->ldo, d->out_is_f32, d->out_scale);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "splitk_finalize launch: %s", cudaGetErrorString(e));
   }
   return MDB_OK;

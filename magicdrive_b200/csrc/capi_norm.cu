@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ beta, int silu,
                                                        __nv_bfloat16* __restrict__ out, int ldo, uint32_t inv_pp) {
   constexpr int T = 256;
+  mdb::pdl_launch_dependents();
+  mdb::pdl_wait();
   extern __shared__ uint32_t slab[];  // [units] bf16x2 (CACHED only)
   __shared__ float red[T / 32];
   __shared__ float bcast;
@@ -218,6 +220,8 @@ template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, int ldx,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ out, int ldo) {
+  mdb::pdl_launch_dependents();
+  mdb::pdl_wait();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -295,9 +299,9 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
         cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr = true;
       }
-      gn_fused_kernel<true><<<dim3(groups, n_img), 256, slab_bytes, st>>>(
-          static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
-          gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo, inv_pp);
+      launch_pdl(gn_fused_kernel<true>, dim3(groups, n_img), dim3(256), slab_bytes, st,
+                 static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups,
+                 eps, gamma, beta, silu, static_cast<__nv_bfloat16*>(out), ldo, inv_pp);
     } else {
       gn_fused_kernel<false><<<dim3(groups, n_img), 256, 0, st>>>(
           static_cast<const __nv_bfloat16*>(x0), c0, ld0, static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps,
@@ -343,11 +347,11 @@ extern "C" int mdb_layernorm(const void* x, long long rows, int c, int ldx, cons
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
   if (nvec <= 64)
-    layernorm_kernel<2><<<blocks, warps * 32, 0, st>>>(xp, rows, c, ldx, gamma, beta, eps, op, ldo);
+    launch_pdl(layernorm_kernel<2>, dim3(blocks), dim3(warps * 32), 0, st, xp, rows, c, ldx, gamma, beta, eps, op, ldo);
   else if (nvec <= 160)
-    layernorm_kernel<5><<<blocks, warps * 32, 0, st>>>(xp, rows, c, ldx, gamma, beta, eps, op, ldo);
+    launch_pdl(layernorm_kernel<5>, dim3(blocks), dim3(warps * 32), 0, st, xp, rows, c, ldx, gamma, beta, eps, op, ldo);
   else
-    layernorm_kernel<8><<<blocks, warps * 32, 0, st>>>(xp, rows, c, ldx, gamma, beta, eps, op, ldo);
+    launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(warps * 32), 0, st, xp, rows, c, ldx, gamma, beta, eps, op, ldo);
   MDB_CHECK_LAUNCH("layernorm_kernel");
   return MDB_OK;
 }

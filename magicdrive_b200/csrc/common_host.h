@@ -39,6 +39,39 @@ inline EncodeTiledFn get_encode() {
 }  // namespace mdb
 #endif
 
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#include <stdlib.h>
+namespace mdb {
+// Programmatic dependent launch: the kernel may start while its stream predecessor drains; every kernel launched
+// this way executes griddepcontrol.wait before touching global memory (see pdl_wait() in ptx.cuh / kernels).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDB_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+}  // namespace mdb
+#endif
+
 #define MDB_CHECK_LAUNCH(name)                                                                   \
   do {                                                                                           \
     cudaError_t e__ = cudaGetLastError();                                                        \

@@ -8,6 +8,7 @@
 //   warp 0: TMA producer      warp 1: MMA issuer      warps 2..5: epilogue (TMEM lane quarter = warp & 3)
 #pragma once
 #include "gemm_tc.cuh"
+#include "common_host.h"
 
 namespace mdb {
 
@@ -47,6 +48,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   long long* trace = (p.trace != nullptr && blockIdx.x < 8) ? p.trace + blockIdx.x * 16 : nullptr;
 #define MDB_TRACE(slot) do { if (trace) trace[slot] = clock64(); } while (0)
   if (threadIdx.x == 0) MDB_TRACE(0);
@@ -79,6 +81,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) MDB_TRACE(1);
+  // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the predecessor's tail; from here on
+  // we read its outputs / overwrite buffers it may still be reading
+  pdl_wait();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
