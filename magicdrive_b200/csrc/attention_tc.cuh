@@ -97,7 +97,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_free = bars + 8;        // softmax -> MMA: O_j consumed (count 4 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * ATT_BM;
   const int ntiles = (p.lk + ATT_BN - 1) / ATT_BN;

@@ -133,7 +133,6 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ beta, int silu,
                                                        __nv_bfloat16* __restrict__ out, int ldo, uint32_t inv_pp) {
   constexpr int T = 256;
-  mdb::pdl_launch_dependents();
   mdb::pdl_wait();
   extern __shared__ uint32_t slab[];  // [units] bf16x2 (CACHED only)
   __shared__ float red[T / 32];
@@ -220,7 +219,6 @@ template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, int ldx,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ out, int ldo) {
-  mdb::pdl_launch_dependents();
   mdb::pdl_wait();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;

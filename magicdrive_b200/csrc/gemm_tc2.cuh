@@ -48,7 +48,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
   long long* trace = (p.trace != nullptr && blockIdx.x < 8) ? p.trace + blockIdx.x * 16 : nullptr;
 #define MDB_TRACE(slot) do { if (trace) trace[slot] = clock64(); } while (0)
   if (threadIdx.x == 0) MDB_TRACE(0);
@@ -192,6 +191,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
+      if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_launch_dependents();  // last tile of this CTA: let the next grid stage
       if (warp == 2 && lane == 0 && it == 0) MDB_TRACE(7);
       const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
