@@ -35,10 +35,14 @@ struct AttnTcCfg {
   static constexpr int TILE = ATT_BM * 128;  // bytes of one [128 rows][64 bf16] swizzled tile
   static constexpr int SMEM_Q = KD * TILE;
   static constexpr int SMEM_KV = STAGES * 2 * KD * TILE;
-  static constexpr int kSmemBytes = SMEM_Q + SMEM_KV + 1024 + 128;
-  static constexpr int S_COL = 0;         // S: 128 fp32 columns; P (bf16 pairs) aliases columns [0, 64)
-  static constexpr int O_COL = ATT_BN;    // O: D16 fp32 columns
-  static constexpr int kTmemCols = (ATT_BN + D16 <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = SMEM_Q + SMEM_KV + 1024 + 128 + 2 * 2 * ATT_BM * 4 /*row-max exchange*/;
+  static constexpr int S_COL = 0;               // S: 128 fp32 columns
+  static constexpr int P_COL = ATT_BN;          // P: 64 columns of bf16 pairs (own region: the two column-halves of the
+                                                // softmax run concurrently, so P may not alias S)
+  static constexpr int O_COL = ATT_BN + 64;     // O: D16 fp32 columns
+  static constexpr int kTmemCols = (ATT_BN + 64 + D16 <= 256) ? 256 : 512;
+  static constexpr int HW = D16 / 2;            // O columns owned by each softmax half
+  static constexpr int kThreads = 64 + 8 * 32;  // TMA warp, MMA warp, 8 softmax warps
 };
 
 // TS form: A operand from tensor memory
@@ -77,7 +81,7 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr_b
 }
 
 template <int D>
-__global__ void __launch_bounds__(192, (D <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(AttnTcCfg<D>::kThreads, (D <= 64) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using Cfg = AttnTcCfg<D>;
@@ -96,6 +100,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_full = bars + 7;        // MMA -> softmax: O_j ready
   uint64_t* o_free = bars + 8;        // softmax -> MMA: O_j consumed (count 4 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* xchg = reinterpret_cast<float*>(bars + 16);  // [2 buffers][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * ATT_BM;
@@ -114,9 +119,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
-    mbar_init(o_free, 4);
+    mbar_init(o_free, 8);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -191,7 +196,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int k = 0; k < ATT_BN / 16; ++k) {
           // A: P bf16 pairs, 8 TMEM columns per 16 keys; B: V tile rows k*16.. (2048 B per 16 keys)
           const uint64_t bdesc = make_sw128_mnmajor_desc(smem_u32(smV + stage * KD * TILE), TILE) + (2048u >> 4) * k;
-          umma_bf16_ts(tmem_o, tmem_s + 8 * k, bdesc, idesc_o, k > 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_o, tmem_base + Cfg::P_COL + 8 * k, bdesc, idesc_o, k > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[stage]);
@@ -210,89 +215,115 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else {
-    // =========================== softmax + epilogue (warps 2..5) ===========================
+    // =========================== softmax + epilogue (warps 2..9) ===========================
+    // Two warps per TMEM lane quarter: `hlf` 0 owns S columns [0,64) / O columns [0,HW), `hlf` 1 the rest.  One query
+    // row per thread; the row max is exchanged between the two halves through shared memory once per tile, the row
+    // sums only once per set.
+    constexpr int HW = Cfg::HW;
     const int q = warp & 3;
+    const int hlf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t tmem_s = lane_base + Cfg::S_COL;
-    const uint32_t tmem_o = lane_base + Cfg::O_COL;
+    const uint32_t tmem_s = lane_base + Cfg::S_COL + hlf * 64;
+    const uint32_t tmem_p = lane_base + Cfg::P_COL + hlf * 32;
+    const uint32_t tmem_o = lane_base + Cfg::O_COL + hlf * HW;
     const int qrow = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.lq + qrow) * p.ldo + head * D;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.lq + qrow) * p.ldo + head * D + hlf * HW;
+    constexpr int NVALID = (D - HW >= HW) ? HW : (D - HW);  // valid output columns of half 1 (half 0 always has HW)
+    const int nvalid = hlf ? NVALID : HW;
+    const float sc = p.scale_log2;
     int it = 0;
     for (int set = 0; set < p.n_sets; ++set) {
-      float o[D16];
+      float o[HW];
 #pragma unroll
-      for (int i = 0; i < D16; ++i) o[i] = 0.f;
+      for (int i = 0; i < HW; ++i) o[i] = 0.f;
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < ntiles; ++j, ++it) {
         mbar_wait(s_full, it & 1);
         tc_fence_after();
-        const int kbase = j * ATT_BN;
-        const bool tail = (kbase + ATT_BN > p.lk);
-        // ---- pass 1: row max
-        float mx = m;
+        const int kbase = j * ATT_BN + hlf * 64;   // first key of this thread's 64 columns
+        const bool tail = (kbase + 64 > p.lk);
+        // ---- pass 1: raw row max over the own 64 columns
+        float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < ATT_BN; c += 32) {
+        for (int c = 0; c < 64; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_s + c, v);
           tmem_ld_wait();
+          if (!tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = __uint_as_float(v[i]) * p.scale_log2;
-            if (tail && kbase + c + i >= p.lk) s = -INFINITY;
-            mx = fmaxf(mx, s);
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
           }
         }
-        const float corr = exp2f(m - mx);
-        m = mx;
-        // ---- pass 2: p = exp2(s - m), row sum, bf16 pairs back into TMEM columns [0, 64)
+        float* xb = xchg + (it & 1) * 256;
+        xb[hlf * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        mx = fmaxf(mx, xb[(hlf ^ 1) * 128 + row]);
+        const float m_new = fmaxf(m, mx * sc);  // sc > 0
+        const float corr = exp2f(m - m_new);
+        m = m_new;
+        // ---- pass 2: p = exp2(s*sc - m), row sum, bf16 pairs into the P region
         float rs = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < ATT_BN; c += 32) {
+        for (int c = 0; c < 64; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_s + c, v);
           tmem_ld_wait();
           uint32_t pk[16];
+          if (!tail) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float s0 = __uint_as_float(v[i]) * p.scale_log2, s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-            if (tail) {
-              if (kbase + c + i >= p.lk) s0 = -INFINITY;
-              if (kbase + c + i + 1 >= p.lk) s1 = -INFINITY;
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = exp2f(fmaf(__uint_as_float(v[i]), sc, -m_new));
+              const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -m_new));
+              rs += p0 + p1;
+              pk[i >> 1] = pack_bf16(p0, p1);
             }
-            const float p0 = exp2f(s0 - mx), p1 = exp2f(s1 - mx);
-            rs += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = (kbase + c + i < p.lk) ? exp2f(fmaf(__uint_as_float(v[i]), sc, -m_new)) : 0.f;
+              const float p1 = (kbase + c + i + 1 < p.lk) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -m_new)) : 0.f;
+              rs += p0 + p1;
+              pk[i >> 1] = pack_bf16(p0, p1);
+            }
           }
-          // columns c/2 .. c/2+15 of the P region; these alias S columns [c/2, c/2+16) which this thread has already
-          // consumed in this pass (c/2 + 16 <= c + 32 and every earlier chunk is done)
-          tmem_st_32x16(tmem_s + (c >> 1), pk);
+          tmem_st_32x16(tmem_p + (c >> 1), pk);
         }
         tmem_st_wait();
         l = l * corr + rs;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
-        // ---- O_j
+        // ---- O_j (own HW columns)
         mbar_wait(o_full, it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < D16; c += 16) {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem_o + c, v);
+        for (int c = 0; c < HW; c += 8) {
+          uint32_t v[8];
+          tmem_ld_32x8(tmem_o + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(v[i]);
+          for (int i = 0; i < 8; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(v[i]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_free);
       }
-      // ---- finalise this set
-      const float inv = 1.0f / l;
+      // ---- finalise this set: total row sum = both halves
+      float* xb = xchg + (it & 1) * 256;  // `it` parity alternates per tile, so this buffer is not in flight
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // partner has finished reading the last row max
+      xb[hlf * 128 + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const float inv = 1.0f / (l + xb[(hlf ^ 1) * 128 + row]);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // both read before the next set reuses the buffer
       if (qrow < p.lq) {
 #pragma unroll
-        for (int c = 0; c < D; c += 8) {
+        for (int c = 0; c < HW; c += 8) {
+          if (c >= nvalid) break;
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = o[c + i] * inv;

@@ -309,7 +309,7 @@ int launch_attention_tc(const void* q, int ldq, const void* k, int ldk, const vo
   p.ldo = ldo, p.lq = lq, p.lk = lk, p.kv_index = kv_index, p.n_sets = n_sets;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
-  cudaError_t le = mdb::launch_pdl(mdb::attention_tc_kernel<D>, grid, dim3(192), Cfg::kSmemBytes, st, tq, tk, tv, p);
+  cudaError_t le = mdb::launch_pdl(mdb::attention_tc_kernel<D>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tq, tk, tv, p);
   if (le != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc_kernel launch: %s", cudaGetErrorString(le));
   MDB_CHECK_LAUNCH("attention_tc_kernel");
   return MDB_OK;

@@ -133,6 +133,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes
 // (64 bf16) and which was written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for 128B swizzle, K-major)
