@@ -61,18 +61,19 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
-// bf16 output rounding): 2 MUFU + ~12 FP32 ops instead of the ~30-instruction erff() that made the GEGLU epilogue
-// instruction-bound (38 instructions per output element, profiles/).
+// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 plus the
+// ~1e-7 relative error of the approximate rcp / ex2 units: far below the bf16 output rounding).  2 MUFU + 11 FP32 ops;
+// erff() costs ~30 instructions and made the GEGLU epilogue instruction-bound (38 instr / output element).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float hx = 0.5f * x;
   return fmaf(hx, copysignf(erf_abs, x), hx);

@@ -235,64 +235,61 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           }
         }
       } else {
-        // TMEM loads are software-pipelined: the next chunk's tcgen05.ld is in flight while this chunk's bias /
-        // residual math and global stores execute (tcgen05.wait::ld was the top stall of the 4-warp version).
-        uint32_t vnext[32];
-        const bool partial = (p.epi_mode == EPI_PARTIAL_F32);
-        int c = eg * 32;
-        if (c < BLOCK_N && n0 + c < p.n_out && !(p.debug_flags & 4)) tmem_ld_32x32(lane_addr + c, vnext);
 #pragma unroll 1
-        for (; c < BLOCK_N; c += 64) {
+        for (int c = eg * 32; c < BLOCK_N; c += 64) {
           __syncwarp();
           if (warp == 2 && lane == 0 && it == 0 && trace && c < 192) trace[12 + c / 64] = clock64();
           const int col0 = n0 + c;
           if (col0 >= p.n_out) break;  // warp-uniform: nothing left in this tile
           const bool full = (col0 + 32 <= p.n_out);
-          // ---- 1. issue every global load of this chunk before anything consumes one
+          if (p.epi_mode == EPI_PARTIAL_F32) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_addr + c, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float* dst = p.partial + (static_cast<long long>(z) * pixels_total + pix) * p.n_out + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.n_out)
+                  *reinterpret_cast<float4*>(dst + j) =
+                      make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                  __uint_as_float(v[j + 3]));
+              }
+            }
+            continue;
+          }
+          // ---- 1. issue every global load of this chunk before anything consumes one (the old per-column guards
+          //         serialised ~20 load latencies per chunk: 18k cycles per tile on the K=320 GEMMs)
           float4 bv[8], rv[8];
           uint4 res[4];
           const int ncol4 = full ? 8 : (p.n_out - col0) / 4;  // valid float4 groups (n_out % 8 == 0)
-          const bool use_bias = (p.bias != nullptr) && !partial && !(p.debug_flags & 2);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int jj = (j < ncol4) ? j : 0;  // clamp: always a valid address, never stored when out of range
-            bv[j] = use_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[j] = (p.bias && !(p.debug_flags & 2)) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          const bool use_rb = (p.rowbias != nullptr) && row_ok && !partial && !(p.debug_flags & 2);
+          const bool use_rb = (p.rowbias != nullptr) && row_ok && !(p.debug_flags & 2);
           if (use_rb) {
             const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + col0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(rb + 4 * ((j < ncol4) ? j : 0)));
           }
-          const bool use_res = (p.residual != nullptr) && row_ok && !partial && !(p.debug_flags & 2);
+          const bool use_res = (p.residual != nullptr) && row_ok && !(p.debug_flags & 2);
           if (use_res) {
             const __nv_bfloat16* rs = p.residual + pix * p.ldr + col0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(rs + 8 * ((2 * j < ncol4) ? j : 0)));
           }
-          // ---- 2. accumulator of this chunk (already in flight) ; start the next chunk's load
+          // ---- 2. accumulator
           uint32_t v[32];
           if (!(p.debug_flags & 4)) {
+            tmem_ld_32x32(lane_addr + c, v);
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = vnext[j];
-            if (c + 64 < BLOCK_N && n0 + c + 64 < p.n_out) tmem_ld_32x32(lane_addr + c + 64, vnext);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u + j;
           }
           if (!row_ok) continue;
-          if (partial) {
-            float* dst = p.partial + (static_cast<long long>(z) * pixels_total + pix) * p.n_out + col0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j < ncol4)
-                *reinterpret_cast<float4*>(dst + 4 * j) =
-                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                __uint_as_float(v[4 * j + 3]));
-            }
-            continue;
-          }
           // ---- 3. math
           float f[32];
           const float* bvf = reinterpret_cast<const float*>(bv);
@@ -338,7 +335,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
           }
         }
-        tmem_ld_wait();  // a prefetched load may still be in flight when the loop exits early
       }
       // release this accumulator stage to the MMA warp
       tc_fence_before();
