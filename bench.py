@@ -287,9 +287,16 @@ def main():
     gf, gs = sum(f for f, _ in g), sum(s for _, s in g)
     af, as_ = sum(f for f, _ in a), sum(s for _, s in a)
     achieved = gf / gs / 1e12 if gs > 0 else 0.0
+    traffic = None
+    try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (tools/traffic_from_ncu.py)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv, all shapes of one step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
-                "launches": len(g), "flops_per_step": gf, "kernel_ms_per_step": gs * 1e3, "traffic": None,
+                "launches": len(g), "flops_per_step": gf, "kernel_ms_per_step": gs * 1e3, "traffic": traffic,
+                "timing_note": "per-launch CUDA events on an eager pass: short launches include host enqueue latency, so "
+                               "`achieved` is a lower bound; profiles/shape_times_*.txt has ncu device times per shape",
                 "attention": {"achieved": (af / as_ / 1e12 if as_ > 0 else 0.0), "launches": len(a),
                               "kernel_ms_per_step": as_ * 1e3, "flops_per_step": af},
                 "whole_step": {"algorithmic_tflop": TFLOP_PER_SCENE_STEP_CFG[args.res] * args.scenes,
