@@ -41,6 +41,8 @@ ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--debug-flags", type=int, default=0)
+ap.add_argument("--bn", type=int, default=0)
+ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--trace", action="store_true", help="print per-CTA clock64 phase stamps of the persistent kernel")
 ap.add_argument("--profile", action="store_true", help="one launch per shape between cudaProfilerStart/Stop (for ncu)")
 args = ap.parse_args()
@@ -59,7 +61,8 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
         wt, b = pack_geglu(wt, b)
     r = torch.randn(pix, co, device=dev, generator=g).bfloat16() if res else None
     kw = dict(n_img=n, h_in=h, w_in=w, c0=ci, lda0=ci, n_out=co, taps=taps, pad=taps // 2, bias=b, residual=r,
-              ldr=co if res else 0, geglu=geglu, kernel_variant=args.variant, debug_flags=args.debug_flags)
+              ldr=co if res else 0, geglu=geglu, kernel_variant=args.variant, debug_flags=args.debug_flags,
+              force_block_n=0 if geglu else args.bn, force_splits=0 if geglu else args.splits)
     for _ in range(3):
         ops.gemm_conv(x, wt, **kw)
     torch.cuda.synchronize()

@@ -39,6 +39,8 @@ torch.cuda.synchronize()
 if args.events:
     from magicdrive_b200 import ops
     import collections
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(50e6))  # enqueue the whole step behind a spin so events see no host gaps
     ops.start_profile()
     pipe.run_steps(st, 2, 3)
     rec = ops.stop_profile(with_info=True)
