@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--res", default="224x400", choices=["224x400", "424x800"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run ControlNet and UNet encoder on one stream")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -168,7 +169,7 @@ def main():
     ccfg = arch.ControlNetConfig(map_size=(8, 200, 200) if args.res == "224x400" else (8, 400, 400))
     un = UNet2DConditionModelMultiview(**asdict(ucfg)).reset_parameters_synthetic(11).to(dev, torch.bfloat16)
     cn = BEVControlNetModel(**asdict(ccfg)).reset_parameters_synthetic(12).to(dev, torch.bfloat16)
-    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph)
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph, overlap_controlnet=not args.no_overlap)
     inp, h, w = make_inputs(args, rank)
     boxes = inp["bboxes_3d_data"]
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}

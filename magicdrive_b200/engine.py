@@ -316,11 +316,20 @@ class UNetEngine(_Net):
                 mid_res: Optional[torch.Tensor] = None, temb_all: Optional[torch.Tensor] = None) -> torch.Tensor:
         """latents [n*h*w, 64] bf16 (channel-padded) -> predicted noise fp32 [n*h*w, 8] (first out_channels valid).
         `temb_all` may carry precomputed time-embedding projections ([1 or n, sum(cout)] fp32)."""
-        cfg = self.cfg
         if temb_all is None:
             temb_all = self.time_embed(t_f32)
+        x, skips = self.forward_encoder(latents_pad, n, h, w, temb_all, ctx_kv, lc)
+        return self.forward_decoder(x, skips, temb_all, ctx_kv, lc, down_res, mid_res)
+
+    def forward_encoder(self, latents_pad, n, h, w, temb_all, ctx_kv, lc):
+        """conv_in + down blocks + mid block: independent of the ControlNet residuals, so the pipeline runs it
+        concurrently with the ControlNet on a second stream."""
         x = self.conv_in(latents_pad, n, h, w)
-        x, skips = self.encoder(x, temb_all, ctx_kv, lc)
+        return self.encoder(x, temb_all, ctx_kv, lc)
+
+    def forward_decoder(self, x, skips, temb_all, ctx_kv, lc, down_res=None, mid_res=None) -> torch.Tensor:
+        cfg = self.cfg
+        skips = list(skips)
         if down_res is not None:
             skips = [FMap(ops.add(s.data, r), s.n, s.h, s.w, s.c) for s, r in zip(skips, down_res)]
         if mid_res is not None:

@@ -266,7 +266,9 @@ class BEVControlNetModel(_B200Module):
         ret = dict()
         ret["camera_param"] = torch.cat([self.uncond_cam_param([batch_size, n_cam]).to(camera_param), camera_param])
         if bboxes_3d_data is None:
-            logging.warning("Your 'bboxes_3d_data' should not be None. If this warning keeps popping, please check your code.")
+            if not getattr(self, "_warned_no_boxes", False):  # the reference logs this on every call; once is enough
+                logging.warning("Your 'bboxes_3d_data' should not be None. If this warning keeps popping, please check your code.")
+                self._warned_no_boxes = True
             if max_len is not None:
                 dev = camera_param.device
                 ret["bboxes_3d_data"] = {

@@ -74,11 +74,28 @@ def _need_cuda(*ts):
 
 
 _ws = {}
+_ws_slot = 0
+
+
+class workspace_slot:
+    """Select which split-K scratch buffer the enclosed launches use (slot 1 = the concurrent ControlNet stream)."""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+    def __enter__(self):
+        global _ws_slot
+        self.prev, _ws_slot = _ws_slot, self.slot
+
+    def __exit__(self, *a):
+        global _ws_slot
+        _ws_slot = self.prev
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
     """Per-device scratch (split-K partials); grown on demand outside CUDA-graph capture."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    # one scratch per (device, slot): split-K GEMMs may run concurrently on the ControlNet / UNet streams
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _ws_slot)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
@@ -168,6 +185,22 @@ def conv_direct(x, wgt, bias, *, n, h, w, cin, cout, k, stride=(1, 1), pad=(1, 1
 
 
 _gn_ws = {}
+_ws_slot = 0
+
+
+class workspace_slot:
+    """Select which split-K scratch buffer the enclosed launches use (slot 1 = the concurrent ControlNet stream)."""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+    def __enter__(self):
+        global _ws_slot
+        self.prev, _ws_slot = _ws_slot, self.slot
+
+    def __exit__(self, *a):
+        global _ws_slot
+        _ws_slot = self.prev
 
 
 def groupnorm(x0, c0, ld0, n_img, hw, gamma, beta, eps, silu, x1=None, c1=0, ld1=0, groups=32):

@@ -47,13 +47,22 @@ class BEVControlNetDenoiser:
     """Call-compatible core of StableDiffusionBEVControlNetPipeline for `output_type="latent"` with precomputed
     prompt embeddings (the CLIP text encoder and the VAE sit outside the hot path: SURVEY.md §2.1)."""
 
-    def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True):
+    def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True,
+                 overlap_controlnet: bool = True):
         self.unet, self.controlnet = unet, controlnet
+        self.overlap_controlnet = overlap_controlnet
+        self._side = {}
         self.scheduler = DDIMSchedule()
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._graph_key = None
         self._static = None
+
+    def _side_stream(self, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
 
     # ------------------------------------------------------------------ one step on resident buffers
     def _step(self, st):
@@ -62,9 +71,23 @@ class BEVControlNetDenoiser:
         lat = st["latents"]  # fp32 [S*ncam*h*w, 4] NHWC, S scenes (no CFG duplication)
         # bf16, channel-padded to one K block; CFG: [uncond ; cond] share the latents (:352-354) -> repeat = 2
         x = ops.pack_latents(lat, ue.CIN_PAD, repeat=2 if st["cfg"] else 1)
-        down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
-                                     temb_all=st.get("c_temb"))
-        eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid, temb_all=st.get("u_temb"))
+        if self.overlap_controlnet and st.get("u_temb") is not None:
+            # The ControlNet and the UNet's down/mid path only meet at the skip additions: run them on two streams so
+            # that each one's small-grid kernels and per-kernel tails are filled by the other (captured as two branches
+            # of the same CUDA graph).
+            main = torch.cuda.current_stream()
+            side = self._side_stream(lat.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.workspace_slot(1):
+                down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
+                                             temb_all=st["c_temb"])
+            xe, skips = ue.forward_encoder(x, V, h, w, st["u_temb"], st["u_kv"], st["lc"])
+            main.wait_stream(side)
+            eps = ue.forward_decoder(xe, skips, st["u_temb"], st["u_kv"], st["lc"], down, mid)
+        else:
+            down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
+                                         temb_all=st.get("c_temb"))
+            eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid, temb_all=st.get("u_temb"))
         ops.cfg_ddim_step(eps, lat, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
 
     @torch.no_grad()
