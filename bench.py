@@ -269,6 +269,7 @@ def main():
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): per-launch CUDA events, eager pass
     pipe.use_cuda_graph = False
+    overlap_was, pipe.overlap_controlnet = pipe.overlap_controlnet, False  # serial launches: per-kernel times are not inflated by co-running kernels
     st = prepare()
     pipe.set_schedule(st, 50)
     run(0)
@@ -280,6 +281,7 @@ def main():
     run(1)
     prof = ops.stop_profile()
     pipe.use_cuda_graph = was
+    pipe.overlap_controlnet = overlap_was
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -327,7 +329,8 @@ def main():
                                       "note": "every step also re-stages ALL conditioning inputs from the host and re-runs "
                                               "the camera/box/map encoders and the 23 context K/V projections"},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "cpu_baseline": cpu, "cuda_graph": not args.no_graph}
+                "roofline": roofline, "cpu_baseline": cpu, "cuda_graph": not args.no_graph,
+                "two_stream_overlap": not args.no_overlap}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -27,7 +27,7 @@ args = ap.parse_args()
 dev = torch.device("cuda", 0)
 un = UNet2DConditionModelMultiview(**asdict(arch.UNetConfig())).reset_parameters_synthetic(11).to(dev, torch.bfloat16)
 cn = BEVControlNetModel(**asdict(arch.ControlNetConfig())).reset_parameters_synthetic(12).to(dev, torch.bfloat16)
-pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False)
+pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False)
 inp = synthetic_inputs(args.scenes, 6, 28, 50, n_box=20 if args.workload == "full" else 0, map_hw=200, seed=0)
 if args.workload == "cam":
     inp["bev_map"] = torch.zeros_like(inp["bev_map"])
