@@ -94,7 +94,22 @@ def run_reference_cpu(args, steps, warmup):
     """The reference's CPU path restated (oracle/torch_oracle.py, fp32, torch CPU kernels on all host threads)."""
     from magicdrive_b200 import arch
     from oracle import torch_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    # all host threads the arithmetic can actually use: torch's CPU conv/GEMM stop scaling (and regress) well before
+    # 128 threads on this workload, so the thread count is calibrated on a representative 3x3 conv first
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (ncpu, ncpu // 2, ncpu // 4, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
+    xcal, wcal = torch.randn(12, 320, 28, 50), torch.randn(320, 320, 3, 3)
+    best_t, best_c = None, ncpu
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(xcal, wcal, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            torch.nn.functional.conv2d(xcal, wcal, padding=1)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_t, best_c = dt, c
+    torch.set_num_threads(best_c)
     ucfg, ccfg = arch.UNetConfig(), arch.ControlNetConfig(map_size=(8, 200, 200) if args.res == "224x400" else (8, 400, 400))
     usd = arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), 11)
     csd = arch.synthetic_state_dict(arch.controlnet_param_shapes(ccfg), 12)
