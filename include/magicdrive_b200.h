@@ -95,14 +95,16 @@ int mdb_layernorm(const void* x, long long rows, int c, int ldx, const float* ga
                   void* out, int ldo, void* stream);
 
 /* Fused multi-head attention forward, softmax(Q K^T * scale) V, bf16 in/out, fp32 softmax.
- * q: [B, Lq, heads*d] with row stride ldq; k, v: [Bkv, Lk, heads*d] with row strides ldk, ldv; out like q (ldo).
- * kv_index: device int32 [B * n_sets] or NULL.  With n_sets == 2 the kernel computes
+ * q: [b, Lq, heads*d] with row stride ldq; k, v: [b_kv, Lk, heads*d] with row strides ldk, ldv; out like q (ldo).
+ * kv_index: device int32 [b * n_sets] of K/V batch indices (< b_kv) or NULL (then b_kv == b and batch i attends to
+ * K/V batch i).  b_kv > b is the view-sharded case: K/V of all views were all-gathered, queries are local.
+ * With n_sets == 2 the kernel computes
  *   out[b] = attn(q[b], kv[kv_index[2b]]) + attn(q[b], kv[kv_index[2b+1]])
  * which is the cross-view "add" mode (magicdrive/networks/blocks.py:112-121, 213-217) without the 2x token
  * duplication.  Replaces xformers efficient_attention_forward_cutlass / F.scaled_dot_product_attention
  * (attention_processor.py:1165-1171, 1252). */
 int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
-                  int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale, void* stream);
+                  int b_kv, int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale, void* stream);
 
 /* out = a + b (bf16), n elements (unet_2d_condition_multiview.py:464-473, 487-488). */
 int mdb_add(const void* a, const void* b, void* out, long long n, void* stream);

@@ -318,18 +318,19 @@ int launch_attention_tc(const void* q, int ldq, const void* k, int ldk, const vo
 }  // namespace
 
 extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
-                             int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale, void* stream) {
+                             int b_kv, int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale,
+                             void* stream) {
   using namespace mdb;
   if (!q || !k || !v || !out) return set_error(MDB_ERR_INVALID, "mdb_attention: null pointer");
   if (n_sets < 1 || n_sets > 2 || (n_sets == 2 && !kv_index))
     return set_error(MDB_ERR_INVALID, "mdb_attention: n_sets must be 1 or 2 (2 needs kv_index)");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return set_error(MDB_ERR_UNSUPPORTED, "mdb_attention: strides must be multiples of 8");
-  if (lq <= 0 || lk <= 0 || b <= 0 || heads <= 0) return set_error(MDB_ERR_INVALID, "mdb_attention: bad shape");
+  if (lq <= 0 || lk <= 0 || b <= 0 || heads <= 0 || b_kv <= 0) return set_error(MDB_ERR_INVALID, "mdb_attention: bad shape");
+  if (!kv_index && b_kv != b) return set_error(MDB_ERR_INVALID, "mdb_attention: b_kv != b needs kv_index");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char* legacy = getenv("MDB_ATTN_LEGACY");
   if (!(legacy && legacy[0] == '1')) {
-    // tcgen05 path.  K/V batch count: the cross-view index addresses views of the same tensor as q.
-    const int b_kv = b;
+    // tcgen05 path
     switch (d) {
       case 40: return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
       case 80: return launch_attention_tc<80>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);

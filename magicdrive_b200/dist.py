@@ -4,8 +4,14 @@ The path shards over (scene, view, cfg-half) samples; the only coupling is cross
 and cfg-half (magicdrive/networks/blocks.py:113-121).  Scene-sharding therefore needs NO data-path collective
 (BASELINE.json configs[4]): every rank denoises its own scenes and the finished latents are
 gathered once.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only for that gather, the barrier
-and the max-over-ranks timing."""
-from typing import List, Tuple
+and the max-over-ranks timing.
+
+`ViewShard` is the second mode (BASELINE.json north_star: "NCCL all-gather of cross-view KV"): the cameras of ONE
+scene are split across ranks, for latency rather than throughput.  Everything on the path is per view except the
+neighbour-view attention, so the only exchange is one all-gather of that block's K/V projections per multiview
+transformer (16 per step); queries, softmax and the output stay local and address the gathered K/V through the
+kernel's kv_index (include/magicdrive_b200.h: mdb_attention, b_kv > b)."""
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -52,3 +58,59 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.item()
+
+
+class ViewShard:
+    """Contiguous split of the n_cam cameras of every scene over the ranks of `group` (n_cam % world == 0).
+
+    Local sample order on every rank is (cfg-half, scene, local view), i.e. the unsharded order with the view axis cut;
+    `all_gather_rows` stacks the ranks' K/V row blocks in rank order, so the K/V batch of (sample s, global view g) sits
+    at  (g // n_local) * n_samples * n_local + s * n_local + g % n_local  — what `kv_index` returns for the two ring
+    neighbours of each local view (neighboring_view_pair, configs/dataset/Nuscenes.yaml:27-33)."""
+
+    def __init__(self, rank: int, world: int, n_cam: int, group: Optional["dist.ProcessGroup"] = None):
+        if n_cam % world:
+            raise ValueError(f"view sharding needs n_cam ({n_cam}) divisible by the group size ({world})")
+        self.rank, self.world, self.n_cam, self.group = rank, world, n_cam, group
+        self.n_local = n_cam // world
+
+    @property
+    def views(self) -> Tuple[int, int]:
+        return self.rank * self.n_local, (self.rank + 1) * self.n_local
+
+    def gathered_batch(self, sample: int, view: int, n_samples: int) -> int:
+        r, j = divmod(view, self.n_local)
+        return r * n_samples * self.n_local + sample * self.n_local + j
+
+    def kv_index(self, n_local_views: int, pairs: Sequence[Sequence[int]]) -> List[List[int]]:
+        assert n_local_views % self.n_local == 0 and len(pairs) == self.n_cam
+        n_samples = n_local_views // self.n_local
+        b, _ = self.views
+        return [[self.gathered_batch(s, pairs[b + j][0], n_samples), self.gathered_batch(s, pairs[b + j][1], n_samples)]
+                for s in range(n_samples) for j in range(self.n_local)]
+
+    def slice_views(self, inputs: dict) -> dict:
+        """Cut the view axis (dim 1) of camera_param / bboxes_3d_data / 5-D latents; per-scene tensors pass through."""
+        b, e = self.views
+        n_cam = self.n_cam
+
+        def cut(k, v):
+            if isinstance(v, dict):
+                return {kk: cut(kk, x) for kk, x in v.items()}
+            if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == n_cam and (k != "latents" or v.dim() == 5) \
+                    and k not in ("prompt_embeds", "negative_prompt_embeds", "image", "bev_map"):
+                return v[:, b:e]
+            return v
+        return {k: cut(k, v) for k, v in inputs.items()}
+
+    def all_gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """[rows, cols] contiguous -> [world * rows, cols], rank-major, on the current stream."""
+        out = torch.empty((self.world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    def gather_views(self, local: torch.Tensor) -> torch.Tensor:
+        """(S, n_local, ...) per rank -> (S, n_cam, ...) on every rank."""
+        bufs = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(bufs, local.contiguous(), group=self.group)
+        return torch.cat(bufs, dim=1)

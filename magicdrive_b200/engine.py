@@ -135,6 +135,7 @@ class _Net:
         self.resnets: List[arch.ResnetSpec] = [rs for b in self.down for rs, _ in b.layers] + [self.mid[0], self.mid[2]]
         self.transformers: List[arch.TransformerSpec] = [tr for b in self.down for _, tr in b.layers if tr] + [self.mid[1]]
         self._kv_idx = {}
+        self.view_shard = None  # dist.ViewShard when the cameras of a scene are split across ranks
 
     # ---------------------------------------------------------------- time embedding
     def _finalize_specs(self):
@@ -193,10 +194,18 @@ class _Net:
         if n_views not in self._kv_idx:
             nb = self.cfg.neighboring_view_pair
             n_cam = len(nb)
-            assert n_views % n_cam == 0
-            idx = [[s * n_cam + nb[i][0], s * n_cam + nb[i][1]] for s in range(n_views // n_cam) for i in range(n_cam)]
+            if self.view_shard is not None:  # indices into the all-gathered K/V (dist.ViewShard)
+                idx = self.view_shard.kv_index(n_views, [nb[i] for i in range(n_cam)])
+            else:
+                assert n_views % n_cam == 0
+                idx = [[s * n_cam + nb[i][0], s * n_cam + nb[i][1]] for s in range(n_views // n_cam) for i in range(n_cam)]
             self._kv_idx[n_views] = torch.tensor(idx, dtype=torch.int32, device=self.device)
         return self._kv_idx[n_views]
+
+    def set_view_shard(self, shard) -> None:
+        """Split the cameras across ranks (dist.ViewShard) or back to all views on this GPU (None)."""
+        self.view_shard = shard
+        self._kv_idx = {}
 
     def context_kv(self, ctx_bf16: torch.Tensor) -> Dict[str, torch.Tensor]:
         """attn2 K/V projections of the conditioning tokens for every transformer (step-invariant).
@@ -248,10 +257,19 @@ class _Net:
                                           "configs/model/SDv1.5mv_rawbox.yaml:19-20) is implemented")
             g, b = W.norm(blk + ".norm4")
             n4 = ops.layernorm(X, g, b)
-            wqkv = W.cat_lin(blk + ".attn4.wqkv", [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
-            qkv = ops.linear(n4, wqkv)
-            o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C, ldk=3 * C,
-                              ldv=3 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
+            if self.view_shard is None:
+                wqkv = W.cat_lin(blk + ".attn4.wqkv", [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
+                qkv = ops.linear(n4, wqkv)
+                o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C,
+                                  ldk=3 * C, ldv=3 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
+            else:
+                # cameras split across ranks: local queries, K/V of every rank's views all-gathered over NVLink
+                wq, _ = W.lin(blk + ".attn4.to_q", bias=False)
+                wkv = W.cat_lin(blk + ".attn4.wkv", [blk + ".attn4.to_k", blk + ".attn4.to_v"])
+                q = ops.linear(n4, wq)
+                kv = self.view_shard.all_gather_rows(ops.linear(n4, wkv))
+                o = ops.attention(q, kv, kv[:, C:], b=V, b_kv=V * self.view_shard.world, heads=heads, lq=L, lk=L, d=d,
+                                  ldq=C, ldk=2 * C, ldv=2 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
             wf, bf_ = W.folded_connector(blk)
             X = ops.linear(o, wf, bias=bf_, residual=X)
         # --- GEGLU feed-forward

@@ -225,15 +225,16 @@ def layernorm(x, gamma, beta, eps=1e-5):
     return out
 
 
-def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=None, n_sets=1, out=None):
-    """q: [b*lq, >=heads*d] view with row stride ldq, k/v likewise; returns [b*lq, heads*d] bf16."""
+def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=None, n_sets=1, out=None, b_kv=None):
+    """q: [b*lq, >=heads*d] view with row stride ldq, k/v [b_kv*lk, ...] likewise; returns [b*lq, heads*d] bf16."""
+    b_kv = b if b_kv is None else b_kv
     global _launches
     _need_cuda(q, k, v)
     if out is None:
         out = torch.empty((b * lq, heads * d), dtype=BF16, device=q.device)
     e0 = _prof_begin()
-    check(_lib.lib().mdb_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), out.stride(0), b, heads, lq, lk,
-                                   d, _ptr(kv_index), n_sets, float(scale), _stream()), "mdb_attention")
+    check(_lib.lib().mdb_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), out.stride(0), b, b_kv, heads, lq,
+                                   lk, d, _ptr(kv_index), n_sets, float(scale), _stream()), "mdb_attention")
     _prof_end("attention", 4.0 * b * heads * lq * lk * d * n_sets, e0, f"B={b} H={heads} Lq={lq} Lk={lk} D={d} sets={n_sets}")
     _launches += 1
     return out

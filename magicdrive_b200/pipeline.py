@@ -48,9 +48,13 @@ class BEVControlNetDenoiser:
     prompt embeddings (the CLIP text encoder and the VAE sit outside the hot path: SURVEY.md §2.1)."""
 
     def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True,
-                 overlap_controlnet: bool = True):
+                 overlap_controlnet: bool = True, view_shard=None):
+        """view_shard: a dist.ViewShard to split the cameras of each scene across the ranks of its group (inputs are
+        still passed with all n_cam views on every rank; the result is gathered back to (S, n_cam, ...))."""
         self.unet, self.controlnet = unet, controlnet
         self.overlap_controlnet = overlap_controlnet
+        self.view_shard = view_shard
+        unet.engine().set_view_shard(view_shard)
         self._side = {}
         self.scheduler = DDIMSchedule()
         self.use_cuda_graph = use_cuda_graph
@@ -98,6 +102,11 @@ class BEVControlNetDenoiser:
         dev = self.unet.device
         cn, un = self.controlnet, self.unet
         cfg = guidance_scale > 1.0
+        if self.view_shard is not None:
+            if latents.dim() == 4:
+                latents = torch.stack([latents] * camera_param.shape[1], dim=1)
+            cut = self.view_shard.slice_views(dict(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, latents=latents))
+            camera_param, bboxes_3d_data, latents = cut["camera_param"], cut["bboxes_3d_data"], cut["latents"]
         camera_param = camera_param.to(dev, F32)
         S, n_cam = camera_param.shape[:2]
         prompt_embeds = prompt_embeds.to(dev, F32)
@@ -195,7 +204,7 @@ class BEVControlNetDenoiser:
         self.run_steps(st, 0, num_inference_steps)
         return self.latents_out(st)
 
-    @staticmethod
-    def latents_out(st):
+    def latents_out(self, st):
         S, n_cam, h, w = st["S"], st["n_cam"], st["h"], st["w"]
-        return st["latents"].view(S, n_cam, h, w, -1).permute(0, 1, 4, 2, 3).contiguous()
+        out = st["latents"].view(S, n_cam, h, w, -1).permute(0, 1, 4, 2, 3).contiguous()
+        return out if self.view_shard is None else self.view_shard.gather_views(out)

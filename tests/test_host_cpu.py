@@ -53,7 +53,7 @@ def test_errors_are_reported_not_swallowed():
     d = _lib.GemmDesc()
     rc = L.mdb_gemm_conv(ctypes.byref(d), None)
     assert rc != 0 and b"null pointer" in L.mdb_last_error()
-    assert L.mdb_attention(None, 8, None, 8, None, 8, None, 8, 1, 1, 1, 1, 40, None, 1, 1.0, None) != 0
+    assert L.mdb_attention(None, 8, None, 8, None, 8, None, 8, 1, 1, 1, 1, 1, 40, None, 1, 1.0, None) != 0
 
 
 @pytest.mark.parametrize("name", ["sd15", "tiny"])

@@ -5,6 +5,7 @@ Tolerance: bf16 storage cannot meet rtol 1e-3 / atol 1e-4 elementwise (the refer
 its fp32 forward by more, SURVEY.md §7 "Tolerance"); the criterion is  err(ours-bf16 vs fp32 truth) <=
 1.5 x err(reference-arithmetic-in-bf16 vs fp32 truth) + 2e-3, where "reference arithmetic in bf16" is the oracle
 restatement run with bf16 weights/activations through torch's own CUDA kernels."""
+import os
 from dataclasses import asdict
 
 import pytest
@@ -140,3 +141,18 @@ def test_sd15_forward_vs_fp32_oracle(cuda_lib, h, w, map_hw):
     ok = torch.isclose(eps.float(), e32, rtol=1e-3, atol=1e-4).float().mean().item()
     ok_ref = torch.isclose(ye.float(), e32, rtol=1e-3, atol=1e-4).float().mean().item()
     print(f"[parity] literal rtol1e-3/atol1e-4 pass fraction: ours {ok:.3f}, reference-bf16 {ok_ref:.3f}")
+
+
+@pytest.mark.gpu
+def test_view_sharded_cross_view_attention_two_gpus():
+    """Cameras split across 2 GPUs, cross-view K/V all-gathered over NCCL, vs the single-GPU path (tools/check_view_shard.py)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_view_shard.py")],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
