@@ -143,6 +143,40 @@ def test_sd15_forward_vs_fp32_oracle(cuda_lib, h, w, map_hw):
     print(f"[parity] literal rtol1e-3/atol1e-4 pass fraction: ours {ok:.3f}, reference-bf16 {ok_ref:.3f}")
 
 
+def _tiny_case(scenes, n_box, seed, masks_off=False):
+    from magicdrive_b200.synthetic import synthetic_inputs
+    inp = synthetic_inputs(scenes, 6, 10, 13, n_box=n_box, map_hw=52, seed=seed)
+    if masks_off and inp["bboxes_3d_data"] is not None:
+        inp["bboxes_3d_data"]["masks"][:] = False
+    return inp
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("case", ["no_cfg_no_boxes", "cfg_two_scenes", "cfg_all_boxes_masked", "reuse_graph_new_inputs"])
+def test_tiny_pipeline_edge_cases_vs_oracle(cuda_lib, case):
+    """Paths the reference pipeline takes besides the fixture's: guidance <= 1 (no CFG batch, :352), bboxes_3d_data=None
+    (unet_addon_rawbox.py:790-797), every box masked out, several scenes per call, and a second call on the same
+    denoiser (resident buffers refreshed in place under the captured graph)."""
+    ucfg, ccfg = tiny_configs()
+    usd, csd = tiny_state_dicts(21)
+    un, cn = _models(ucfg, ccfg, usd, csd)
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=True)
+    runs = {"no_cfg_no_boxes": [(_tiny_case(1, 0, 31), 1.0)],
+            "cfg_two_scenes": [(_tiny_case(2, 3, 32), 2.0)],
+            "cfg_all_boxes_masked": [(_tiny_case(1, 3, 33, masks_off=True), 3.5)],
+            "reuse_graph_new_inputs": [(_tiny_case(1, 3, 34), 2.0), (_tiny_case(1, 3, 35), 2.0)]}[case]
+    for k, (inp, guidance) in enumerate(runs):
+        truth = O.denoise_loop(usd, csd, ucfg, ccfg, inp["latents"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                               inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], 3, guidance)
+        out = pipe(image=inp["bev_map"], camera_param=inp["camera_param"], prompt_embeds=inp["prompt_embeds"],
+                   negative_prompt_embeds=inp["negative_prompt_embeds"], latents=inp["latents"], num_inference_steps=3,
+                   guidance_scale=guidance, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
+        assert out.shape == truth.shape
+        e = rel_l2(out, truth)
+        print(f"[parity] edge case {case}[{k}]: rel-L2 {e:.3e} max-rel {max_rel(out, truth):.3e}")
+        assert e < 2e-2
+
+
 @pytest.mark.gpu
 def test_view_sharded_cross_view_attention_two_gpus():
     """Cameras split across 2 GPUs, cross-view K/V all-gathered over NCCL, vs the single-GPU path (tools/check_view_shard.py)."""
