@@ -4,10 +4,11 @@ The library is the product: there is no Python / torch fallback.  `lib()` raises
 and every wrapper raises `MdbError` when a call returns a non-zero status.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 _LIB = None
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmagicdrive_b200.so"
+LIB_PATH = Path(os.environ.get("MDB_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libmagicdrive_b200.so")  # env: A/B builds
 
 
 class MdbError(RuntimeError):

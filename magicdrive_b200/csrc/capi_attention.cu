@@ -14,7 +14,9 @@
 #include "../../include/magicdrive_b200.h"
 #define MDB_NEED_TENSORMAP
 #include "common_host.h"
+#include <string.h>
 #include "attention_tc.cuh"
+#include "attention_tc2.cuh"
 
 namespace {
 
@@ -315,6 +317,47 @@ int launch_attention_tc(const void* q, int ldq, const void* k, int ldk, const vo
   return MDB_OK;
 }
 
+// Second-generation kernel (attention_tc2.cuh), head dim <= 80.
+template <int D, bool DOUBLE_S>
+int launch_attention_tc2(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
+                         int heads, int lq, int lk, int b_kv, const int* kv_index, int n_sets, float scale, cudaStream_t st) {
+  using Cfg = mdb::AttnTc2Cfg<D, DOUBLE_S>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mdb::attention_tc2_kernel<D, DOUBLE_S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc2 smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  CUtensorMap tq, tk, tv;
+  if (!make_qkv_map(&tq, q, D, heads, lq, b, ldq) || !make_qkv_map(&tk, k, D, heads, lk, b_kv, ldk) ||
+      !make_qkv_map(&tv, v, D, heads, lk, b_kv, ldv))
+    return mdb::set_error(MDB_ERR_CUDA, "mdb_attention: cuTensorMapEncodeTiled failed (d=%d heads=%d lq=%d lk=%d)", D, heads,
+                          lq, lk);
+  mdb::AttnTcParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo, p.lq = lq, p.lk = lk, p.kv_index = kv_index, p.n_sets = n_sets;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
+  cudaError_t le = mdb::launch_pdl(mdb::attention_tc2_kernel<D, DOUBLE_S>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tq, tk, tv, p);
+  if (le != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc2_kernel launch: %s", cudaGetErrorString(le));
+  MDB_CHECK_LAUNCH("attention_tc2_kernel");
+  return MDB_OK;
+}
+
+// Which kernel generation serves a call: MDB_ATTN_KERNEL = tc2 | tc | legacy (A/B switch, read per call).
+enum class AttnKernel { kLegacy, kTc, kTc2, kTc2Double };
+AttnKernel attention_kernel_choice() {
+  const char* legacy = getenv("MDB_ATTN_LEGACY");
+  if (legacy && legacy[0] == '1') return AttnKernel::kLegacy;
+  const char* e = getenv("MDB_ATTN_KERNEL");
+  if (e && !strcmp(e, "legacy")) return AttnKernel::kLegacy;
+  if (e && !strcmp(e, "tc2")) return AttnKernel::kTc2;
+  if (e && !strcmp(e, "tc2d")) return AttnKernel::kTc2Double;
+  if (e && !strcmp(e, "tc")) return AttnKernel::kTc;
+  return AttnKernel::kTc2;  // default: tc2 (two CTAs/SM, one S buffer) for d <= 64, double-buffered S for d = 80, tc for d = 160
+}
+
 }  // namespace
 
 extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
@@ -328,8 +371,21 @@ extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, con
   if (lq <= 0 || lk <= 0 || b <= 0 || heads <= 0 || b_kv <= 0) return set_error(MDB_ERR_INVALID, "mdb_attention: bad shape");
   if (!kv_index && b_kv != b) return set_error(MDB_ERR_INVALID, "mdb_attention: b_kv != b needs kv_index");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* legacy = getenv("MDB_ATTN_LEGACY");
-  if (!(legacy && legacy[0] == '1')) {
+  const AttnKernel which = attention_kernel_choice();
+#define MDB_TC2(DD, DBL) \
+  return launch_attention_tc2<DD, DBL>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st)
+  if ((which == AttnKernel::kTc2 || which == AttnKernel::kTc2Double) && scale > 0.f) {
+    const bool dbl = which == AttnKernel::kTc2Double;  // tc2: two CTAs/SM with one S buffer where d <= 64
+    switch (d) {
+      case 40: if (dbl) MDB_TC2(40, true); else MDB_TC2(40, false);
+      case 32: if (dbl) MDB_TC2(32, true); else MDB_TC2(32, false);
+      case 64: if (dbl) MDB_TC2(64, true); else MDB_TC2(64, false);
+      case 80: MDB_TC2(80, true);
+      default: break;  // d = 160 stays on the first tcgen05 kernel
+    }
+  }
+#undef MDB_TC2
+  if (which != AttnKernel::kLegacy) {
     // tcgen05 path
     switch (d) {
       case 40: return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);

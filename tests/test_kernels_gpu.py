@@ -156,11 +156,19 @@ def test_layernorm(cuda_lib, c):
     assert _rel(out, ref) < 8e-3
 
 
-@pytest.mark.parametrize("legacy", [0, 1])  # 0 = tcgen05 kernel (default), 1 = mma.sync kernel
+ATTN_KERNELS = ["tc2", "tc2d", "tc", "legacy"]  # tcgen05 v2 (2 CTAs/SM | double-buffered S; d = 160 falls to tc), tcgen05 v1, mma.sync
+
+
+def _pick_attention_kernel(monkeypatch, kernel):
+    monkeypatch.delenv("MDB_ATTN_LEGACY", raising=False)
+    monkeypatch.setenv("MDB_ATTN_KERNEL", kernel)
+
+
+@pytest.mark.parametrize("kernel", ATTN_KERNELS)
 @pytest.mark.parametrize("d,heads", [(40, 8), (80, 8), (160, 8), (32, 2), (64, 2)])
-@pytest.mark.parametrize("lq,lk", [(1400, 1400), (350, 98), (91, 91), (28, 28), (70, 130), (130, 257)])
-def test_attention(cuda_lib, monkeypatch, d, heads, lq, lk, legacy):
-    monkeypatch.setenv("MDB_ATTN_LEGACY", str(legacy))
+@pytest.mark.parametrize("lq,lk", [(1400, 1400), (350, 98), (91, 91), (28, 28), (70, 130), (130, 257), (200, 40), (129, 600)])
+def test_attention(cuda_lib, monkeypatch, d, heads, lq, lk, kernel):
+    _pick_attention_kernel(monkeypatch, kernel)
     g = torch.Generator(device="cuda").manual_seed(9)
     b = 3
     c = heads * d
@@ -178,11 +186,34 @@ def test_attention(cuda_lib, monkeypatch, d, heads, lq, lk, legacy):
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=5e-3)
 
 
-@pytest.mark.parametrize("legacy", [0, 1])
+@pytest.mark.parametrize("kernel", ATTN_KERNELS)
+@pytest.mark.parametrize("d,heads", [(40, 8), (80, 4)])
+@pytest.mark.parametrize("lq,lk", [(300, 700), (1400, 1400)])
+def test_attention_growing_scores(cuda_lib, monkeypatch, d, heads, lq, lk, kernel):
+    """Scores that grow along the key axis (later key tiles dominate by far more than 2^8): exercises the running-max
+    update of the online softmax, incl. the in-TMEM accumulator rescale of the tc2 kernel."""
+    _pick_attention_kernel(monkeypatch, kernel)
+    g = torch.Generator(device="cuda").manual_seed(19)
+    b = 2
+    c = heads * d
+    q = _bf(torch.randn(b * lq, c, device="cuda", generator=g))
+    ramp = (1.0 + 9.0 * torch.arange(lk, device="cuda") / lk).repeat(b)[:, None]  # |k| x1 .. x10 along the keys
+    k = _bf(torch.randn(b * lk, c, device="cuda", generator=g) * ramp)
+    v = _bf(torch.randn(b * lk, c, device="cuda", generator=g))
+    scale = d ** -0.5
+    out = ops.attention(q, k, v, b=b, heads=heads, lq=lq, lk=lk, d=d, ldq=c, ldk=c, ldv=c, scale=scale)
+    qh = q.float().reshape(b, lq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(b, lk, heads, d).transpose(1, 2)
+    vh = v.float().reshape(b, lk, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(b * lq, c)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=5e-3)
+
+
+@pytest.mark.parametrize("kernel", ATTN_KERNELS)
 @pytest.mark.parametrize("l,heads,d", [(350, 8, 80), (1400, 8, 40), (91, 8, 160)])
-def test_attention_two_sets_cross_view(cuda_lib, monkeypatch, legacy, l, heads, d):
+def test_attention_two_sets_cross_view(cuda_lib, monkeypatch, kernel, l, heads, d):
     """attn4 'add' mode: out[view i] = attn(q_i, kv_left(i)) + attn(q_i, kv_right(i)) (blocks.py:112-121,213-217)."""
-    monkeypatch.setenv("MDB_ATTN_LEGACY", str(legacy))
+    _pick_attention_kernel(monkeypatch, kernel)
     g = torch.Generator(device="cuda").manual_seed(10)
     scenes, ncam = 2, 6
     c = heads * d

@@ -1,5 +1,6 @@
-"""profiles/traffic_rN.json from an `ncu --set full -k regex:gemm_tc2_kernel` capture of one denoising step:
-average DRAM bytes (read + write) and duration per launch of the dominant kernel."""
+"""profiles/traffic_rN.json from an ncu capture (-k regex:gemm_tc2_kernel, default --cache-control all so every replay
+pass starts from a flushed L2) of one denoising step: average DRAM bytes (read + write) and duration per launch of the
+dominant kernel.  usage: traffic_from_ncu.py report.ncu-rep out.json ["note"]"""
 import csv
 import json
 import subprocess
@@ -18,12 +19,13 @@ def col(name):
 
 
 rd, wr, dur = col("dram__bytes_read.sum"), col("dram__bytes_write.sum"), col("gpu__time_duration.sum")
-tp = col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
 n = len(data)
 res = {"kernel": "gemm_tc2_kernel (all instantiations)", "launches_profiled": n,
-       "dram_bytes_per_launch": (sum(rd) + sum(wr)) / n, "dram_read_bytes_per_step": sum(rd), "dram_write_bytes_per_step": sum(wr),
-       "avg_us_per_launch_under_ncu": sum(dur) / n,
-       "tensor_pipe_active_pct_time_weighted": sum(t * d for t, d in zip(tp, dur)) / sum(dur),
-       "source": rep}
+       "dram_bytes_per_launch": (sum(rd) + sum(wr)) / n, "dram_read_bytes_profiled": sum(rd), "dram_write_bytes_profiled": sum(wr),
+       "avg_us_per_launch_under_ncu": sum(dur) / n, "source": rep,
+       "note": sys.argv[3] if len(sys.argv) > 3 else ""}
+if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in hdr:
+    tp = col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    res["tensor_pipe_active_pct_time_weighted"] = sum(t * d for t, d in zip(tp, dur)) / sum(dur)
 json.dump(res, open(out_json, "w"), indent=1)
 print(json.dumps(res))
