@@ -363,7 +363,9 @@ def main():
                 "two_stream_overlap": not args.no_overlap}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        from magicdrive_b200.dist import shutdown
+        sys.stdout.flush()
+        shutdown([pipe])
     return 0
 
 

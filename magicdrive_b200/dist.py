@@ -11,6 +11,10 @@ scene are split across ranks, for latency rather than throughput.  Everything on
 neighbour-view attention, so the only exchange is one all-gather of that block's K/V projections per multiview
 transformer (16 per step); queries, softmax and the output stay local and address the gathered K/V through the
 kernel's kv_index (include/magicdrive_b200.h: mdb_attention, b_kv > b)."""
+import gc
+import os
+import sys
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -50,6 +54,27 @@ def gather_scenes(local: torch.Tensor, n_total: int) -> torch.Tensor:
     bufs: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     return torch.cat([bufs[r][: e - b] for r, (b, e) in enumerate(counts)], dim=0)
+
+
+def shutdown(denoisers=(), timeout_s: float = 20.0) -> None:
+    """Tear the process group down at the end of a run.  A CUDA graph that captured NCCL collectives (view-sharded mode)
+    keeps the communicator busy: release the graphs first; if the communicator still does not come down within
+    `timeout_s` (observed on 2 x B200, NCCL 2.28.9: destroy_process_group never returned with a live graph), flush
+    and leave the process without running the remaining teardown."""
+    for d in denoisers:
+        d.release_graph()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not dist.is_available() or not dist.is_initialized():
+        return
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    if t.is_alive():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def max_over_ranks(value: float, device) -> float:

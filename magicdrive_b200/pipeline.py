@@ -62,6 +62,12 @@ class BEVControlNetDenoiser:
         self._graph_key = None
         self._static = None
 
+    def release_graph(self):
+        """Drop the captured CUDA graph (it is re-captured on the next run_steps)."""
+        self._graph = None
+        self._graph_key = None
+        self._graph_state = None
+
     def _side_stream(self, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in self._side:

@@ -182,11 +182,11 @@ def test_view_sharded_cross_view_attention_two_gpus():
     """Cameras split across 2 GPUs, cross-view K/V all-gathered over NCCL, vs the single-GPU path (tools/check_view_shard.py)."""
     import subprocess
     import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < 2 or os.environ.get("MDB_TEST_MULTI_GPU") != "1":
+        pytest.skip("needs 2 GPUs and MDB_TEST_MULTI_GPU=1 (spawns torchrun; last run: profiles/view_shard_r1.txt)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_view_shard.py")],
                        capture_output=True, text=True, timeout=900, cwd=root)
     print(r.stdout[-2000:], r.stderr[-2000:])
-    assert r.returncode == 0
+    assert r.returncode == 0 and r.stdout.count("OK") >= 4

@@ -13,7 +13,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from magicdrive_b200 import arch  # noqa: E402
-from magicdrive_b200.dist import ViewShard  # noqa: E402
+from magicdrive_b200.dist import ViewShard, shutdown  # noqa: E402
 from magicdrive_b200.models import BEVControlNetModel, UNet2DConditionModelMultiview  # noqa: E402
 from magicdrive_b200.pipeline import BEVControlNetDenoiser  # noqa: E402
 from magicdrive_b200.synthetic import synthetic_inputs  # noqa: E402
@@ -33,16 +33,20 @@ def main():
               guidance_scale=2.0, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
     ref = BEVControlNetDenoiser(un, cn, use_cuda_graph=False)(**kw)
     rc = 0
+    dens = []
     for graph in (False, True):
         den = BEVControlNetDenoiser(un, cn, use_cuda_graph=graph, view_shard=ViewShard(rank, world, 6))
+        dens.append(den)
         out = den(**kw)
         err = ((out - ref).norm() / ref.norm()).item()
         ok = out.shape == ref.shape and err < 2e-2
         print(f"[view-shard] rank {rank}/{world} graph={graph} rel-L2 vs unsharded {err:.3e} {'OK' if ok else 'FAIL'}", flush=True)
         rc |= 0 if ok else 1
     un.engine().set_view_shard(None)
-    dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    if rc:
+        os._exit(rc)
+    shutdown(dens)
     return rc
 
 
