@@ -323,11 +323,11 @@ def main():
     af, as_ = sum(f for f, _ in a), sum(s for _, s in a)
     achieved = gf / gs / 1e12 if gs > 0 else 0.0
     traffic = None
-    try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (tools/traffic_from_ncu.py)
+    try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (tools/traffic_from_ncu.py)
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv, all shapes of one step)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel (persistent tcgen05 GEMM / implicit-GEMM conv, all shapes of one step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
                 "launches": len(g), "flops_per_step": gf, "kernel_ms_per_step": gs * 1e3, "traffic": traffic,
                 "timing_note": "per-launch CUDA events on an eager pass queued behind a spin kernel (no host enqueue gaps); "

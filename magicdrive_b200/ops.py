@@ -5,6 +5,7 @@ torch is plumbing only: it owns device memory and the CUDA stream; every functio
 Feature maps are NHWC bf16 ("channels innermost") everywhere; a token matrix [tokens, C] is the same layout.
 """
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -210,7 +211,7 @@ def groupnorm(x0, c0, ld0, n_img, hw, gamma, beta, eps, silu, x1=None, c1=0, ld1
     stats = torch.empty((n_img * groups * 2,), dtype=F32, device=x0.device)
     check(_lib.lib().mdb_groupnorm(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n_img, hw, groups, float(eps), _ptr(gamma),
                                    _ptr(beta), int(silu), _ptr(out), c0 + c1, _ptr(stats), _stream()), "mdb_groupnorm")
-    _launches += 2  # stats + apply kernels (plus one memset node)
+    _launches += 2 if os.environ.get("MDB_GN_TWO_KERNEL") else 1  # one fused kernel (A/B: stats + apply)
     return out
 
 
