@@ -71,6 +71,9 @@ def resnet_block(sd: SD, p: str, x, temb, groups=32, eps=1e-5):
     return x + h
 
 
+USE_SDPA = False  # tests/test_zz_speed_gpu.py sets it: F.scaled_dot_product_attention, as AttnProcessor2_0 itself calls (:1251)
+
+
 def attention(sd: SD, p: str, x, ctx, heads):
     """Attention + AttnProcessor2_0.__call__, diffusers/models/attention_processor.py:1202-1272."""
     q = _lin(sd, p + ".to_q", x)
@@ -82,8 +85,11 @@ def attention(sd: SD, p: str, x, ctx, heads):
     qh = q.view(b, lq, heads, d).transpose(1, 2)
     kh = k.view(b, -1, heads, d).transpose(1, 2)
     vh = v.view(b, -1, heads, d).transpose(1, 2)
-    s = torch.softmax((qh @ kh.transpose(-1, -2)) * (d ** -0.5), dim=-1)
-    o = (s @ vh).transpose(1, 2).reshape(b, lq, c)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(b, lq, c)
+    else:
+        s = torch.softmax((qh @ kh.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+        o = (s @ vh).transpose(1, 2).reshape(b, lq, c)
     return _lin(sd, p + ".to_out.0", o)
 
 
