@@ -144,6 +144,15 @@ int mdb_pack_latents(const void* x, int x_is_f32, long long pix, int cin, int cp
 int mdb_cfg_ddim_step(const float* eps, int eps_ld, int c, int cfg, float guidance, const float* coef, float* latents,
                       long long n, void* stream);
 
+/* Classifier-free guidance + one UniPCMultistepScheduler step fused (the reference's default sampler,
+ * magicdrive/misc/test_utils.py:129; scheduling_unipc_multistep.py:518-600 with solver_order 2, bh2, predict_x0,
+ * epsilon prediction).  eps as in mdb_cfg_ddim_step.  latents, last_sample, m0, m1: fp32 [n/c, c], all updated in
+ * place (sample, sample before the last predictor, newest and previous x0 prediction; zero them before step 0).
+ * coef: device fp32[12] for this step = {a0, a1, c0, c1, c2, c3, p0, p1, p2, use_corrector, 0, 0}:
+ *   x0 = a0 x + a1 eps;  xc = use_corrector ? c0 last + c1 m0 + c2 m1 + c3 x0 : x;  x' = p0 xc + p1 x0 + p2 m0. */
+int mdb_cfg_unipc_step(const float* eps, int eps_ld, int c, int cfg, float guidance, const float* coef, float* latents,
+                       float* last_sample, float* m0, float* m1, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

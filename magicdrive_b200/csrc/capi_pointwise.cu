@@ -248,6 +248,31 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps, int cfg, float gu
   lat[i] = coef[0] * lat[i] + coef[1] * e;
 }
 
+// Guidance combine + one UniPC (order <= 2, bh2, x0-prediction) step: every update of the multistep scheduler is a
+// linear combination of  x, the previous corrected sample, and the last two x0 predictions  with per-step scalar
+// coefficients (host: pipeline.UniPCSchedule), so corrector + history shift + predictor are one pass over the latents.
+__global__ void cfg_unipc_kernel(const float* __restrict__ eps, int cfg, float guidance, const float* __restrict__ coef,
+                                 float* __restrict__ lat, float* __restrict__ last, float* __restrict__ m0,
+                                 float* __restrict__ m1, long long n, int c, int eps_ld) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long pix = i / c;
+  const int ch = static_cast<int>(i - pix * c);
+  const long long npix = n / c;
+  float e = eps[pix * eps_ld + ch];
+  if (cfg) {
+    const float ec = eps[(npix + pix) * eps_ld + ch];
+    e = e + guidance * (ec - e);
+  }
+  const float x = lat[i], h0 = m0[i], h1 = m1[i];
+  const float x0 = coef[0] * x + coef[1] * e;                                                   // convert_model_output
+  const float xc = (coef[9] != 0.f) ? coef[2] * last[i] + coef[3] * h0 + coef[4] * h1 + coef[5] * x0 : x;  // UniC
+  lat[i] = coef[6] * xc + coef[7] * x0 + coef[8] * h0;                                          // UniP
+  last[i] = xc;
+  m1[i] = h0;
+  m0[i] = x0;
+}
+
 // latents [pix, cin] (fp32 or bf16) -> bf16 [repeat * pix, cpad], channels >= cin zero: the K-padded A operand of the
 // tensor-core conv_in; `repeat` = 2 duplicates the batch for classifier-free guidance ([uncond ; cond] share latents)
 template <typename TI>
@@ -402,5 +427,16 @@ extern "C" int mdb_cfg_ddim_step(const float* eps, int eps_ld, int c, int cfg, f
   cfg_ddim_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, cfg, guidance, coef, latents, n, c,
                                                                                   eps_ld);
   MDB_CHECK_LAUNCH("cfg_ddim_kernel");
+  return MDB_OK;
+}
+
+extern "C" int mdb_cfg_unipc_step(const float* eps, int eps_ld, int c, int cfg, float guidance, const float* coef,
+                                  float* latents, float* last_sample, float* m0, float* m1, long long n, void* stream) {
+  if (!eps || !coef || !latents || !last_sample || !m0 || !m1)
+    return set_error(MDB_ERR_INVALID, "mdb_cfg_unipc_step: null pointer");
+  if (c <= 0 || eps_ld < c || n % c) return set_error(MDB_ERR_INVALID, "mdb_cfg_unipc_step: bad shape");
+  cfg_unipc_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, cfg, guidance, coef, latents,
+                                                                                   last_sample, m0, m1, n, c, eps_ld);
+  MDB_CHECK_LAUNCH("cfg_unipc_kernel");
   return MDB_OK;
 }

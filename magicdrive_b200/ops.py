@@ -332,6 +332,17 @@ def cfg_ddim_step(eps, latents, coef, cfg: bool, guidance: float, c: int = 4):
     return latents
 
 
+def cfg_unipc_step(eps, latents, last_sample, m0, m1, coef, cfg: bool, guidance: float, c: int = 4):
+    """Guidance + one UniPC step; latents / last_sample / m0 / m1 fp32 [pixels, c] updated in place, coef fp32[12]."""
+    global _launches
+    _need_cuda(eps, latents, last_sample, m0, m1, coef)
+    check(_lib.lib().mdb_cfg_unipc_step(_ptr(eps), eps.stride(0), c, int(cfg), float(guidance), _ptr(coef), _ptr(latents),
+                                        _ptr(last_sample), _ptr(m0), _ptr(m1), latents.numel(), _stream()),
+          "mdb_cfg_unipc_step")
+    _launches += 1
+    return latents
+
+
 def pack_latents(x, cpad: int = 64, repeat: int = 1):
     """[pix, cin] fp32/bf16 -> bf16 [repeat*pix, cpad] zero-padded channels."""
     global _launches

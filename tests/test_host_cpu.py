@@ -95,3 +95,27 @@ def test_uncond_helpers_match_reference_fixture():
     assert kw["bboxes_3d_data"]["bboxes"].shape == (2, 6, 9, 8, 3)
     assert not kw["bboxes_3d_data"]["masks"][0].any() and kw["bboxes_3d_data"]["masks"].dtype == torch.bool
     assert torch.equal(kw["bboxes_3d_data"]["classes"][1, :, :5], boxes["classes"][0])
+
+
+def test_unipc_schedule_coefficients_reproduce_the_oracle():
+    """pipeline.UniPCSchedule reduces corrector + history shift + predictor to per-step scalar coefficients; the
+    recurrence mdb_cfg_unipc_step evaluates (include/magicdrive_b200.h), emulated here in torch, must follow the oracle's
+    (= the reference scheduler's) trajectory for every order / warm-up / final-step case."""
+    from magicdrive_b200.pipeline import UniPCSchedule
+    from oracle import torch_oracle as O
+    for n in (20, 50, 5, 3, 2, 1):
+        sch, orc = UniPCSchedule(), O.UniPC()
+        ts = sch.set_timesteps(n)
+        assert ts == orc.set_timesteps(n).tolist() and len(sch.coefs) == len(ts)
+        g = torch.Generator().manual_seed(100 + n)
+        x = torch.randn(2, 4, 10, 13, generator=g)
+        xo, last, m0, m1 = x.clone(), torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
+        for i, t in enumerate(ts):
+            eps = torch.randn(2, 4, 10, 13, generator=g)
+            c = torch.tensor(sch.coefs[i], dtype=torch.float32)
+            assert len(c) == UniPCSchedule.ROW and (c[9] != 0) == (i > 0)
+            x0 = c[0] * x + c[1] * eps
+            xc = c[2] * last + c[3] * m0 + c[4] * m1 + c[5] * x0 if c[9] != 0 else x
+            x, last, m1, m0 = c[6] * xc + c[7] * x0 + c[8] * m0, xc, m0, x0
+            xo = orc.step(eps, t, xo)
+            assert ((x - xo).abs().max() / xo.abs().max()).item() < 1e-5

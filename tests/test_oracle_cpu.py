@@ -168,3 +168,29 @@ def test_oracle_reproduces_reference_encoders_fixture():
                                e["box_emb"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(O.map_encode(csd, ccfg, e["bev_map"].float()), e["map_emb"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(O.uncond_cam_param(csd, ccfg, 2, 6).contiguous(), e["uncond_cam"], rtol=0, atol=0)
+
+
+def test_oracle_unipc_reproduces_reference_scheduler_fixture():
+    """UniPCMultistepScheduler (the reference's default sampler) stepped by the reference itself over seeded tensors
+    (oracle/make_golden_unipc.py): the restatement must follow the whole trajectory, incl. warm-up and final lower order."""
+    cases = golden("unipc_scheduler.pt")
+    for n, c in cases.items():
+        s = O.UniPC()
+        assert torch.equal(s.set_timesteps(n), c["timesteps"])
+        x = c["x"].clone()
+        for i, t in enumerate(c["timesteps"].tolist()):
+            x = s.step(c["eps"][i], t, x)
+            torch.testing.assert_close(x, c["traj"][i], rtol=1e-5, atol=1e-5)
+
+
+@torch.no_grad()
+def test_oracle_reproduces_reference_unipc_pipeline_fixture():
+    """The unmodified reference pipeline with its default UniPC sampler, 4 steps, CFG 2.0 (tiny models)."""
+    p = golden("tiny_pipeline_unipc.pt")
+    inp = golden(p["inputs_from"])["inputs"]
+    ucfg, ccfg = tiny_configs()
+    usd, csd = tiny_state_dicts(p["seed"])
+    out = O.denoise_loop(usd, csd, ucfg, ccfg, inp["latents"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                         inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], p["steps"], p["guidance"],
+                         scheduler="unipc")
+    torch.testing.assert_close(out, p["latents_out"], rtol=1e-3, atol=3e-4 * p["latents_out"].abs().max().item())
