@@ -153,6 +153,13 @@ int mdb_cfg_ddim_step(const float* eps, int eps_ld, int c, int cfg, float guidan
 int mdb_cfg_unipc_step(const float* eps, int eps_ld, int c, int cfg, float guidance, const float* coef, float* latents,
                        float* last_sample, float* m0, float* m1, long long n, void* stream);
 
+/* Given-view generation (magicdrive/pipeline/pipeline_bev_controlnet_given_view.py:263-296, 379-389): for every view v
+ * with view_mask[v] != 0, rows [v*rows_per_view, (v+1)*rows_per_view) of dst (fp32, row stride dst_ld, c channels used)
+ * become coef[0]*a + coef[1]*b; a, b: fp32 [n_views*rows_per_view, c] contiguous, a may be NULL (term dropped);
+ * coef: device fp32[2].  Used to re-noise pinned views (scheduler.add_noise) and to replace their predicted noise. */
+int mdb_pin_views(float* dst, int dst_ld, const float* a, const float* b, int c, const float* coef, const int* view_mask,
+                  long long rows_per_view, int n_views, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

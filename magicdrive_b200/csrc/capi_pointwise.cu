@@ -273,6 +273,22 @@ __global__ void cfg_unipc_kernel(const float* __restrict__ eps, int cfg, float g
   m0[i] = x0;
 }
 
+// rows of the views flagged in view_mask: dst = coef[0] * a + coef[1] * b  (a may be null).  Serves the given-view
+// pipeline: re-noising pinned views (a = clean latents, b = their initial noise, coef = sqrt(abar_t), sqrt(1 - abar_t))
+// and replacing their predicted noise by the initial noise (a = null, coef = {0, 1}).
+__global__ void pin_views_kernel(float* __restrict__ dst, int dst_ld, const float* __restrict__ a,
+                                 const float* __restrict__ b, int c, const float* __restrict__ coef,
+                                 const int* __restrict__ view_mask, long long rows_per_view, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long row = i / c;
+  const int ch = static_cast<int>(i - row * c);
+  if (!view_mask[row / rows_per_view]) return;
+  float v = coef[1] * b[i];
+  if (a) v += coef[0] * a[i];
+  dst[row * dst_ld + ch] = v;
+}
+
 // latents [pix, cin] (fp32 or bf16) -> bf16 [repeat * pix, cpad], channels >= cin zero: the K-padded A operand of the
 // tensor-core conv_in; `repeat` = 2 duplicates the batch for classifier-free guidance ([uncond ; cond] share latents)
 template <typename TI>
@@ -438,5 +454,16 @@ extern "C" int mdb_cfg_unipc_step(const float* eps, int eps_ld, int c, int cfg, 
   cfg_unipc_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, cfg, guidance, coef, latents,
                                                                                    last_sample, m0, m1, n, c, eps_ld);
   MDB_CHECK_LAUNCH("cfg_unipc_kernel");
+  return MDB_OK;
+}
+
+extern "C" int mdb_pin_views(float* dst, int dst_ld, const float* a, const float* b, int c, const float* coef,
+                             const int* view_mask, long long rows_per_view, int n_views, void* stream) {
+  if (!dst || !b || !coef || !view_mask) return set_error(MDB_ERR_INVALID, "mdb_pin_views: null pointer");
+  if (c <= 0 || dst_ld < c || rows_per_view <= 0 || n_views <= 0) return set_error(MDB_ERR_INVALID, "mdb_pin_views: bad shape");
+  const long long n = rows_per_view * n_views * c;
+  pin_views_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, dst_ld, a, b, c, coef, view_mask,
+                                                                                   rows_per_view, n);
+  MDB_CHECK_LAUNCH("pin_views_kernel");
   return MDB_OK;
 }

@@ -343,6 +343,17 @@ def cfg_unipc_step(eps, latents, last_sample, m0, m1, coef, cfg: bool, guidance:
     return latents
 
 
+def pin_views(dst, a, b, coef, view_mask, rows_per_view: int, c: int = 4):
+    """dst[rows of flagged views, :c] = coef[0]*a + coef[1]*b  (a may be None); dst fp32 [n_views*rows_per_view, ld>=c]."""
+    global _launches
+    _need_cuda(dst, b, coef, view_mask)
+    assert view_mask.dtype == torch.int32 and dst.shape[0] == view_mask.numel() * rows_per_view
+    check(_lib.lib().mdb_pin_views(_ptr(dst), dst.stride(0), _ptr(a), _ptr(b), c, _ptr(coef), _ptr(view_mask),
+                                   rows_per_view, view_mask.numel(), _stream()), "mdb_pin_views")
+    _launches += 1
+    return dst
+
+
 def pack_latents(x, cpad: int = 64, repeat: int = 1):
     """[pix, cin] fp32/bf16 -> bf16 [repeat*pix, cpad] zero-padded channels."""
     global _launches

@@ -40,6 +40,9 @@ class DDIMSchedule:
             c1 = (1 - a_p) ** 0.5 - (a_p * (1 - a_t) / a_t) ** 0.5
             coefs.append([float(c0), float(c1)])
         self.coefs = coefs
+        # scheduler.add_noise (scheduling_ddim.py:447-470): x_t = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise
+        self.noise_coefs = [[float(self.alphas_cumprod[t] ** 0.5), float((1 - self.alphas_cumprod[t]) ** 0.5)]
+                            for t in self.timesteps]
         return self.timesteps
 
 
@@ -121,6 +124,7 @@ class UniPCSchedule:
                 row[8] = -0.5 * a_p * B_h / rk
             coefs.append(row)
         self.timesteps, self.coefs = ts, coefs
+        self.noise_coefs = [[float(al[t]), float(sg[t])] for t in ts]  # add_noise (:618-640)
         return ts
 
 
@@ -164,6 +168,10 @@ class BEVControlNetDenoiser:
         ue, ce = st["ue"], st["ce"]
         V, h, w = st["V"], st["h"], st["w"]
         lat = st["latents"]  # fp32 [S*ncam*h*w, 4] NHWC, S scenes (no CFG duplication)
+        pin = st.get("pin")
+        if pin is not None and pin["mode"] == "change":
+            # given views are re-noised from their clean latents at every step (pipeline_bev_controlnet_given_view.py:283-296)
+            ops.pin_views(lat, pin["cond"], pin["noise0"], pin["coef_dev"], pin["mask"], h * w, c=lat.shape[1])
         # bf16, channel-padded to one K block; CFG: [uncond ; cond] share the latents (:352-354) -> repeat = 2
         x = ops.pack_latents(lat, ue.CIN_PAD, repeat=2 if st["cfg"] else 1)
         if self.overlap_controlnet and st.get("u_temb") is not None:
@@ -183,6 +191,13 @@ class BEVControlNetDenoiser:
             down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
                                          temb_all=st.get("c_temb"))
             eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid, temb_all=st.get("u_temb"))
+        if pin is not None and pin["mode"] == "once":
+            # given views follow their own initial noise instead of the prediction (:379-389): overwrite both guidance
+            # halves, so the combine u + s (c - u) returns exactly that noise
+            npix = lat.shape[0]
+            for half in range(2 if st["cfg"] else 1):
+                ops.pin_views(eps[half * npix:(half + 1) * npix], None, pin["noise0"], pin["one"], pin["mask"], h * w,
+                              c=lat.shape[1])
         if self.scheduler_name == "ddim":
             ops.cfg_ddim_step(eps, lat, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
         else:
@@ -191,9 +206,11 @@ class BEVControlNetDenoiser:
 
     @torch.no_grad()
     def prepare(self, latents, prompt_embeds, negative_prompt_embeds, camera_param, bboxes_3d_data, image,
-                guidance_scale=2.0, controlnet_conditioning_scale=1.0):
+                guidance_scale=2.0, controlnet_conditioning_scale=1.0, conditional_latents=None,
+                conditional_latents_change_every_input=True):
         """Host -> device staging + all step-invariant work.  latents: (S, 4, h, w) initial noise shared by the views
-        (:326) or (S, n_cam, 4, h, w)."""
+        (:326) or (S, n_cam, 4, h, w).  conditional_latents: list[S] of list[n_cam] of clean (4, h, w) latents or None
+        (StableDiffusionBEVControlNetGivenViewPipeline, pipeline_bev_controlnet_given_view.py:36-37)."""
         dev = self.unet.device
         cn, un = self.controlnet, self.unet
         cfg = guidance_scale > 1.0
@@ -202,6 +219,9 @@ class BEVControlNetDenoiser:
                 latents = torch.stack([latents] * camera_param.shape[1], dim=1)
             cut = self.view_shard.slice_views(dict(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, latents=latents))
             camera_param, bboxes_3d_data, latents = cut["camera_param"], cut["bboxes_3d_data"], cut["latents"]
+            if conditional_latents is not None:
+                vb, ve = self.view_shard.views
+                conditional_latents = [row[vb:ve] for row in conditional_latents]
         camera_param = camera_param.to(dev, F32)
         S, n_cam = camera_param.shape[:2]
         prompt_embeds = prompt_embeds.to(dev, F32)
@@ -223,11 +243,24 @@ class BEVControlNetDenoiser:
         S_, _, c, h, w = lat.shape
         lat_nhwc = lat.reshape(S * n_cam, c, h, w).permute(0, 2, 3, 1).contiguous().view(-1, c)
         V = S * n_cam * (2 if cfg else 1)
-        sig = (V, h, w, cfg, lc, S, n_cam)
+        pin_mode, pin_mask, pin_cond = None, None, None
+        if conditional_latents is not None and any(c is not None for row in conditional_latents for c in row):
+            if len(conditional_latents) != S or any(len(row) != n_cam for row in conditional_latents):
+                raise ValueError("conditional_latents must be a list[scenes] of list[n_cam] of (4, h, w) tensors or None")
+            pin_mode = "change" if conditional_latents_change_every_input else "once"
+            pin_mask = torch.tensor([int(c is not None) for row in conditional_latents for c in row], dtype=torch.int32, device=dev)
+            pin_cond = torch.stack([torch.zeros(c, h, w) if x is None else x.to("cpu", F32)
+                                    for row in conditional_latents for x in row])
+            pin_cond = pin_cond.to(dev).permute(0, 2, 3, 1).contiguous().view(-1, c)
+        sig = (V, h, w, cfg, lc, S, n_cam, pin_mode)
         st = self._static
         if st is not None and st["sig"] == sig:
             # same shapes as the resident state: refresh its buffers in place so a captured graph stays valid
             st["latents"].copy_(lat_nhwc)
+            if pin_mode is not None:
+                st["pin"]["mask"].copy_(pin_mask)
+                st["pin"]["cond"].copy_(pin_cond)
+                st["pin"]["noise0"].copy_(lat_nhwc)
             st["map"].copy_(cond["map"])
             for k, v in cond["kv"].items():
                 st["c_kv"][k].copy_(v)
@@ -241,7 +274,10 @@ class BEVControlNetDenoiser:
                   lc=lc, map=cond["map"].clone(),
                   t_dev=torch.zeros(V, dtype=F32, device=dev),
                   coef_dev=torch.zeros(len(self._coef_row()), dtype=F32, device=dev),
-                  hist=[torch.zeros_like(lat_nhwc) for _ in range(3)] if self.scheduler_name == "unipc" else [])
+                  hist=[torch.zeros_like(lat_nhwc) for _ in range(3)] if self.scheduler_name == "unipc" else [],
+                  pin=None if pin_mode is None else dict(
+                      mode=pin_mode, mask=pin_mask, cond=pin_cond, noise0=lat_nhwc.clone(),
+                      coef_dev=torch.zeros(2, dtype=F32, device=dev), one=torch.tensor([0.0, 1.0], dtype=F32, device=dev)))
         self._static, self._graph = st, None
         return st
 
@@ -251,6 +287,8 @@ class BEVControlNetDenoiser:
     def _set_step(self, st, i):
         st["t_dev"].copy_(st["t_table"][i], non_blocking=True)
         st["coef_dev"].copy_(st["coef_table"][i], non_blocking=True)
+        if st.get("pin") is not None:
+            st["pin"]["coef_dev"].copy_(st["noise_table"][i], non_blocking=True)
         st["u_temb"].copy_(st["u_temb_table"][i:i + 1], non_blocking=True)
         st["c_temb"].copy_(st["c_temb_table"][i:i + 1], non_blocking=True)
 
@@ -259,6 +297,7 @@ class BEVControlNetDenoiser:
         dev = st["latents"].device
         st["t_table"] = torch.tensor(ts, dtype=F32, device=dev)[:, None].expand(-1, st["V"]).contiguous()
         st["coef_table"] = torch.tensor(self.scheduler.coefs, dtype=F32, device=dev)
+        st["noise_table"] = torch.tensor(self.scheduler.noise_coefs, dtype=F32, device=dev)
         # the time-embedding MLP + all time_emb_proj layers depend only on t: one table for the whole schedule
         # (every view-sample of a step shares t, so one row serves all images: rowbias stride 0)
         tt = torch.tensor(ts, dtype=F32, device=dev)
@@ -278,6 +317,11 @@ class BEVControlNetDenoiser:
                 for h in st["hist"]:  # multistep history starts empty (scheduling_unipc_multistep.py:211-217)
                     h.zero_()
             self._set_step(st, i)
+            pin = st.get("pin")
+            if i == 0 and pin is not None and pin["mode"] == "once":
+                # noised once with the first timestep (pipeline_bev_controlnet_given_view.py:264-276)
+                ops.pin_views(st["latents"], pin["cond"], pin["noise0"], pin["coef_dev"], pin["mask"], st["h"] * st["w"],
+                              c=st["latents"].shape[1])
             if not self.use_cuda_graph:
                 self._step(st)
                 continue
@@ -299,13 +343,15 @@ class BEVControlNetDenoiser:
     @torch.no_grad()
     def __call__(self, image, camera_param, prompt_embeds, negative_prompt_embeds=None, latents=None,
                  num_inference_steps: int = 50, guidance_scale: float = 2.0, bev_controlnet_kwargs: Optional[Dict] = None,
-                 controlnet_conditioning_scale: float = 1.0, output_type: str = "latent"):
-        """Same argument meaning as the reference pipeline call (:114-160).  Returns latents (S, n_cam, 4, h, w) fp32."""
+                 controlnet_conditioning_scale: float = 1.0, output_type: str = "latent", conditional_latents=None,
+                 conditional_latents_change_every_input: bool = True):
+        """Same argument meaning as the reference pipeline call (:114-160); with `conditional_latents` it is the
+        given-view pipeline's call (pipeline_bev_controlnet_given_view.py:36-37).  Returns latents (S, n_cam, 4, h, w) fp32."""
         if output_type != "latent":
             raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
         boxes = (bev_controlnet_kwargs or {}).get("bboxes_3d_data")
         st = self.prepare(latents, prompt_embeds, negative_prompt_embeds, camera_param, boxes, image, guidance_scale,
-                          controlnet_conditioning_scale)
+                          controlnet_conditioning_scale, conditional_latents, conditional_latents_change_every_input)
         self.set_schedule(st, num_inference_steps)
         self.run_steps(st, 0, num_inference_steps)
         return self.latents_out(st)

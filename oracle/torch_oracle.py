@@ -315,6 +315,11 @@ class DDIM:
         c1 = (1 - a_p) ** 0.5 - (a_p * (1 - a_t) / a_t) ** 0.5
         return float(c0), float(c1)
 
+    def add_noise(self, x0, noise, t: int):
+        """DDIMScheduler.add_noise (scheduling_ddim.py:447-470)."""
+        a = self.alphas_cumprod[t]
+        return a ** 0.5 * x0 + (1 - a) ** 0.5 * noise
+
     def step(self, eps, t: int, x):
         prev = t - self.T // self.n
         a_t = self.alphas_cumprod[t]
@@ -348,6 +353,10 @@ class UniPC:
         self.last_sample = None
         self.this_order = None
         return self.timesteps
+
+    def add_noise(self, x0, noise, t: int):
+        """UniPCMultistepScheduler.add_noise (scheduling_unipc_multistep.py:618-640)."""
+        return self.alpha_t[t] * x0 + self.sigma_t[t] * noise
 
     def _bh_terms(self, s0, t, order):
         """Shared front part of UniP / UniC: step size in lambda, r_k of the history points, B(h) and the b vector."""
@@ -417,10 +426,15 @@ def add_uncond_to_kwargs(sd: SD, ccfg, camera_param, bboxes_3d_data):
 
 
 def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_prompt_embeds, camera_param,
-                 bboxes_3d_data, bev_map, num_inference_steps, guidance_scale, return_all=False, scheduler="ddim"):
+                 bboxes_3d_data, bev_map, num_inference_steps, guidance_scale, return_all=False, scheduler="ddim",
+                 conditional_latents=None, change_every_input=True):
     """StableDiffusionBEVControlNetPipeline.__call__ steps 5-8 (magicdrive/pipeline/pipeline_bev_controlnet.py:
     303-451) with DDIM eta=0 and output_type='latent'.  latents: (b, 4, h, w) initial noise (shared by the views,
-    :326).  Returns (b, n_cam, 4, h, w)."""
+    :326).  Returns (b, n_cam, 4, h, w).
+    conditional_latents (list[b] of list[n_cam] of (4, h, w) tensor or None) switches to
+    StableDiffusionBEVControlNetGivenViewPipeline.__call__ (pipeline_bev_controlnet_given_view.py:263-296, 379-389):
+    the given views are re-noised from their clean latents every step (change_every_input, the default) or noised
+    once and then driven by their own initial noise instead of the predicted one."""
     sched = DDIM() if scheduler == "ddim" else UniPC()
     timesteps = sched.set_timesteps(num_inference_steps)
     n_cam = camera_param.shape[1]
@@ -431,7 +445,17 @@ def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_
     cam, boxes = (add_uncond_to_kwargs(csd, ccfg, camera_param, bboxes_3d_data) if cfg_on
                   else (camera_param, bboxes_3d_data))
     hist = []
+    pinned = [(i, j) for i, row in enumerate(conditional_latents or []) for j, c in enumerate(row) if c is not None]
+    noise0 = lat.clone()
+    if pinned and not change_every_input:
+        lat = lat.clone()
+        for i, j in pinned:
+            lat[i, j] = sched.add_noise(conditional_latents[i][j], noise0[i, j], int(timesteps[0]))
     for t in timesteps.tolist():
+        if pinned and change_every_input:
+            lat = lat.clone()
+            for i, j in pinned:
+                lat[i, j] = sched.add_noise(conditional_latents[i][j], noise0[i, j], t)
         inp = torch.cat([lat] * 2) if cfg_on else lat
         tt = torch.full((inp.shape[0],), t, dtype=torch.int64)
         down, mid, ctx = controlnet_forward(csd, ccfg, inp, tt, cam, boxes, text, image)
@@ -440,6 +464,11 @@ def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_
         if cfg_on:
             eu, ec = eps.chunk(2)
             eps = eu + guidance_scale * (ec - eu)
+        if pinned and not change_every_input:
+            eps = eps.reshape(lat.shape).clone()
+            for i, j in pinned:
+                eps[i, j] = noise0[i, j]
+            eps = eps.reshape(-1, *lat.shape[2:])
         flat = lat.reshape(-1, *lat.shape[2:])
         lat = sched.step(eps, t, flat).reshape(lat.shape)
         if return_all:

@@ -3,6 +3,7 @@
 here by replaying the reference constructors' RNG order with plain torch.nn layers; (b) fixtures produced by running
 the reference itself (tests/golden/*.pt <- oracle/make_golden.py)."""
 import numpy as np
+import pytest
 import torch
 import torch.nn as nn
 
@@ -194,3 +195,21 @@ def test_oracle_reproduces_reference_unipc_pipeline_fixture():
                          inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], p["steps"], p["guidance"],
                          scheduler="unipc")
     torch.testing.assert_close(out, p["latents_out"], rtol=1e-3, atol=3e-4 * p["latents_out"].abs().max().item())
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("case,scheduler,change", [("ddim_change", "ddim", True), ("ddim_once", "ddim", False),
+                                                   ("unipc_change", "unipc", True)])
+def test_oracle_reproduces_reference_given_view_fixture(case, scheduler, change):
+    """StableDiffusionBEVControlNetGivenViewPipeline.__call__ run by the reference (oracle/make_golden_given_view.py):
+    views 0 and 3 pinned to clean latents, both re-noising modes."""
+    from oracle.make_golden_given_view import pinned_latents
+    p = golden("tiny_given_view.pt")
+    inp = golden(p["inputs_from"])["inputs"]
+    ucfg, ccfg = tiny_configs()
+    usd, csd = tiny_state_dicts(p["seed"])
+    out = O.denoise_loop(usd, csd, ucfg, ccfg, inp["latents"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                         inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], p["steps"], p["guidance"],
+                         scheduler=scheduler, conditional_latents=pinned_latents(p["pinned_seed"]), change_every_input=change)
+    ref = p["outputs"][case]
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=3e-4 * ref.abs().max().item())
