@@ -292,9 +292,20 @@ class BEVControlNetModel(_B200Module):
             ret[k] = v
         return ret
 
+    @torch.no_grad()
     def prepare(self, cfg, **kwargs):
-        """Class tokens come from the checkpoint (use_text_encoder_init=False at inference); nothing to do."""
-        return None
+        """BEVControlNetModel.prepare -> ContinuousBBoxWithTextEmbedding.prepare / set_category_token
+        (unet_addon_rawbox.py:704-705, bbox_embedder.py:117-136): with `use_text_encoder_init` the class tokens are the
+        pooled CLIP embeddings of the dataset's class names (done once before training; checkpoints already carry them)."""
+        if not self.config["bbox_embedder_param"].get("use_text_encoder_init", False):
+            return
+        tokenizer, text_encoder = kwargs["tokenizer"], kwargs["text_encoder"]
+        tokens = self.bbox_embedder._class_tokens
+        for idx, name in enumerate(cfg.dataset.object_classes):
+            ids = tokenizer([name], padding="do_not_pad", return_tensors="pt").input_ids.to(tokens.device)
+            tokens[idx].copy_(text_encoder(ids).pooler_output[0])
+        self._engine = None  # weights changed: repack on the next use
+        self._ctx_cache = {}
 
     # ---------------------------------------------------------------- step-invariant conditioning (cached)
     def _key(self, *ts):

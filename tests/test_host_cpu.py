@@ -119,3 +119,37 @@ def test_unipc_schedule_coefficients_reproduce_the_oracle():
             x, last, m1, m0 = c[6] * xc + c[7] * x0 + c[8] * m0, xc, m0, x0
             xo = orc.step(eps, t, xo)
             assert ((x - xo).abs().max() / xo.abs().max()).item() < 1e-5
+
+
+def test_prepare_initialises_class_tokens_like_the_reference():
+    """BEVControlNetModel.prepare (unet_addon_rawbox.py:704-705 -> bbox_embedder.py:117-136) with stub tokenizer / encoder."""
+    from types import SimpleNamespace
+
+    from magicdrive_b200 import models
+    names = ["car", "truck", "bus"]
+
+    class Tok:
+        def __call__(self, texts, padding, return_tensors):
+            assert padding == "do_not_pad" and return_tensors == "pt"
+            return SimpleNamespace(input_ids=torch.tensor([[49406, 7 + len(texts[0]), 49407]]))
+
+    class Enc:
+        def __call__(self, ids):
+            g = torch.Generator().manual_seed(int(ids[0, 1]))
+            return SimpleNamespace(pooler_output=torch.randn(1, 768, generator=g))
+
+    cfg = SimpleNamespace(dataset=SimpleNamespace(object_classes=names))
+    _, ccfg = tiny_configs()
+    cn = models.BEVControlNetModel(**asdict(ccfg), bbox_embedder_param=dict(n_classes=10, class_token_dim=768,
+                                                                            use_text_encoder_init=True))
+    cn.reset_parameters_synthetic(1)
+    before = cn.bbox_embedder._class_tokens.clone()
+    cn.prepare(cfg, tokenizer=Tok(), text_encoder=Enc())
+    after = cn.bbox_embedder._class_tokens
+    for i, n in enumerate(names):
+        assert torch.equal(after[i], Enc()(Tok()([n], "do_not_pad", "pt").input_ids).pooler_output[0])
+    assert torch.equal(after[len(names):], before[len(names):])
+    cn2 = models.BEVControlNetModel(**asdict(ccfg))  # use_text_encoder_init absent -> untouched
+    cn2.reset_parameters_synthetic(1)
+    cn2.prepare(cfg, tokenizer=None, text_encoder=None)
+    assert torch.equal(cn2.bbox_embedder._class_tokens, before)
