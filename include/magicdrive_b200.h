@@ -94,6 +94,11 @@ int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, int c1, int l
 int mdb_layernorm(const void* x, long long rows, int c, int ldx, const float* gamma, const float* beta, float eps,
                   void* out, int ldo, void* stream);
 
+/* Row softmax of fp32 scores into bf16 probabilities: out[r, j] = softmax_j(s[r, :cols]) for j < cols and 0 for
+ * cols <= j < cols_out (K padding of the following P.V GEMM).  Used by the VAE decoder's single-head 512-wide attention
+ * (unet_2d_blocks.py:433-446; attention_processor.py:1252), whose QK^T and PV products run on mdb_gemm_conv. */
+int mdb_softmax_rows(const float* s, int lds, long long rows, int cols, void* out, int ldo, int cols_out, void* stream);
+
 /* Fused multi-head attention forward, softmax(Q K^T * scale) V, bf16 in/out, fp32 softmax.
  * q: [b, Lq, heads*d] with row stride ldq; k, v: [b_kv, Lk, heads*d] with row strides ldk, ldv; out like q (ldo).
  * kv_index: device int32 [b * n_sets] of K/V batch indices (< b_kv) or NULL (then b_kv == b and batch i attends to

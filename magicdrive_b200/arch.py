@@ -304,6 +304,67 @@ def controlnet_param_shapes(cfg: ControlNetConfig) -> "OrderedDict[str, tuple]":
     return sh
 
 
+# ------------------------------------------------------------------------------------------ VAE decoder
+@dataclass
+class VaeConfig:
+    """AutoencoderKL config of SD-1.5 (third_party/diffusers/src/diffusers/models/autoencoder_kl.py:66-82); only the
+    decoder half is on the path (pipeline_bev_controlnet.py:100-112)."""
+    in_channels: int = 3
+    out_channels: int = 3
+    down_block_types: Tuple[str, ...] = ("DownEncoderBlock2D",) * 4
+    up_block_types: Tuple[str, ...] = ("UpDecoderBlock2D",) * 4
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    act_fn: str = "silu"
+    latent_channels: int = 4
+    norm_num_groups: int = 32
+    sample_size: int = 512
+    scaling_factor: float = 0.18215
+
+
+def vae_decoder_blocks(cfg: VaeConfig):
+    """[(prefix, [(resnet prefix, cin, cout)], upsampler prefix or None)] of Decoder.up_blocks (vae.py:193-219)."""
+    rev = list(reversed(cfg.block_out_channels))
+    blocks, out_c = [], rev[0]
+    for i in range(len(rev)):
+        prev, out_c = out_c, rev[i]
+        res = [(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else out_c, out_c) for j in range(cfg.layers_per_block + 1)]
+        up = None if i == len(rev) - 1 else f"decoder.up_blocks.{i}.upsamplers.0.conv"
+        blocks.append((f"decoder.up_blocks.{i}", res, up))
+    return blocks
+
+
+def vae_decoder_param_shapes(cfg: VaeConfig) -> "OrderedDict[str, tuple]":
+    """Decoder + post_quant_conv keys of AutoencoderKL.state_dict() (vae.py:152-225, autoencoder_kl.py:107-108)."""
+    sh: "OrderedDict[str, tuple]" = OrderedDict()
+    c_mid = cfg.block_out_channels[-1]
+    _conv(sh, "decoder.conv_in", c_mid, cfg.latent_channels, 3)
+
+    def res(p, ci, co):
+        _norm(sh, p + ".norm1", ci)
+        _conv(sh, p + ".conv1", co, ci, 3)
+        _norm(sh, p + ".norm2", co)
+        _conv(sh, p + ".conv2", co, co, 3)
+        if ci != co:
+            _conv(sh, p + ".conv_shortcut", co, ci, 1)
+
+    for _, resnets, up in vae_decoder_blocks(cfg):
+        for p, ci, co in resnets:
+            res(p, ci, co)
+        if up:
+            _conv(sh, up, resnets[-1][2], resnets[-1][2], 3)
+    a = "decoder.mid_block.attentions.0"
+    _norm(sh, a + ".group_norm", c_mid)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        _lin(sh, f"{a}.{n}", c_mid, c_mid)
+    res("decoder.mid_block.resnets.0", c_mid, c_mid)
+    res("decoder.mid_block.resnets.1", c_mid, c_mid)
+    _norm(sh, "decoder.conv_norm_out", cfg.block_out_channels[0])
+    _conv(sh, "decoder.conv_out", cfg.out_channels, cfg.block_out_channels[0], 3)
+    _conv(sh, "post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
+    return sh
+
+
 BUFFER_KEYS = {"bbox_embedder._class_tokens"}
 
 

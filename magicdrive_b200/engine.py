@@ -463,3 +463,104 @@ class ControlNetEngine(_Net):
         wz, bz = self.W.conv("controlnet_mid_block")
         mid = ops.linear(x.data, wz, bias=bz, out_scale=conditioning_scale)
         return down, mid, skips, x
+
+
+class VaeDecoderEngine:
+    """AutoencoderKL.decode for the 6 generated views (pipeline_bev_controlnet.py:100-112 -> autoencoder_kl.py:177-196 ->
+    vae.py:226-273): the step after the denoising path, built from the same operators (implicit-GEMM 3x3 convolutions,
+    single-kernel GroupNorm+SiLU, nearest x2).  The mid block's single-head attention is 512 wide — beyond the fused
+    attention kernels' head dims — and runs as three tensor-core GEMMs per image around a row softmax:
+    S = Q K^T (fp32, scaled), P = softmax(S) (bf16, key count padded to a K block), V^T = W_v X^T, O = P V + b_v."""
+
+    COUT_PAD = 8
+
+    def __init__(self, cfg: arch.VaeConfig, sd, device):
+        self.cfg, self.device = cfg, device
+        self.W = _Weights(sd, device)
+        self.blocks = arch.vae_decoder_blocks(cfg)
+
+    def _resnet(self, p: str, x: FMap, cout: int) -> FMap:
+        """ResnetBlock2D.forward with temb = None (resnet.py:590-640)."""
+        W, g = self.W, self.cfg.norm_num_groups
+        hw = x.h * x.w
+        g1, b1 = W.norm(p + ".norm1")
+        h = ops.groupnorm(x.data, x.c, x.c, x.n, hw, g1, b1, 1e-6, True, groups=g)
+        w1, c1 = W.conv(p + ".conv1")
+        h = ops.gemm_conv(h, w1, n_img=x.n, h_in=x.h, w_in=x.w, c0=x.c, lda0=x.c, n_out=cout, taps=3, pad=1, bias=c1)
+        g2, b2 = W.norm(p + ".norm2")
+        h = ops.groupnorm(h, cout, cout, x.n, hw, g2, b2, 1e-6, True, groups=g)
+        res = x.data
+        if x.c != cout:
+            ws, bs = W.conv(p + ".conv_shortcut")
+            res = ops.gemm_conv(x.data, ws, n_img=x.n, h_in=x.h, w_in=x.w, c0=x.c, lda0=x.c, n_out=cout, bias=bs)
+        w2, c2 = W.conv(p + ".conv2")
+        out = ops.gemm_conv(h, w2, n_img=x.n, h_in=x.h, w_in=x.w, c0=cout, lda0=cout, n_out=cout, taps=3, pad=1, bias=c2,
+                            residual=res, ldr=cout)
+        return FMap(out, x.n, x.h, x.w, cout)
+
+    def _attention(self, x: FMap) -> FMap:
+        """Attention(heads=1, dim_head=C, GroupNorm, residual) of UNetMidBlock2D (unet_2d_blocks.py:433-446)."""
+        W, C, L = self.W, x.c, x.h * x.w
+        a = "decoder.mid_block.attentions.0"
+        g, b = W.norm(a + ".group_norm")
+        t = ops.groupnorm(x.data, C, C, x.n, L, g, b, 1e-6, False, groups=self.cfg.norm_num_groups)
+        wq, bq = W.lin(a + ".to_q")
+        wk, bk = W.lin(a + ".to_k")
+        wv, bv = W.lin(a + ".to_v")
+        q = ops.linear(t, wq, bias=bq)
+        k = ops.linear(t, wk, bias=bk)
+        lp = (L + 63) // 64 * 64  # keys padded to whole K blocks of the P.V product
+        o = torch.empty((x.n * L, C), dtype=q.dtype, device=q.device)
+        for i in range(x.n):
+            rows = slice(i * L, (i + 1) * L)
+            kp = torch.zeros((lp, C), dtype=k.dtype, device=k.device)
+            kp[:L] = k[rows]
+            tp = torch.zeros((lp, C), dtype=t.dtype, device=t.device)
+            tp[:L] = t[rows]
+            s = ops.linear(q[rows], kp, out_f32=True, out_scale=C ** -0.5)          # [L, lp]: q . k_j / sqrt(C)
+            p = ops.softmax_rows(s, L, lp)                                          # bf16, padded keys get 0
+            vt = ops.linear(wv, tp)                                                 # [C, lp] = W_v X^T  (V^T, no bias)
+            ops.linear(p, vt, bias=bv, out=o[rows], ldo=C)                           # P V + b_v (rows of P sum to 1)
+        wo, bo = W.lin(a + ".to_out.0")
+        out = ops.linear(o, wo, bias=bo, residual=x.data)
+        return FMap(out, x.n, x.h, x.w, C)
+
+    def decode(self, z_nhwc: torch.Tensor, n: int, h: int, w: int, scale: float = 1.0, to_unit_range: bool = False):
+        """z_nhwc: fp32 [n*h*w, 4] latents (the denoiser's resident layout); `scale` multiplies them first
+        (1 / scaling_factor).  Returns fp32 [n, 8h, 8w, 3] (with to_unit_range: image / 2 + 0.5 clamped to [0, 1])."""
+        cfg, W = self.cfg, self.W
+        key = ("pq", float(scale))
+        if key not in W.t:  # 1x1 post_quant_conv with the latent scale folded into its weights
+            W.t[key] = (_f32(W.raw("post_quant_conv.weight").float().permute(0, 2, 3, 1) * scale), _f32(W.raw("post_quant_conv.bias")))
+        wq, bq = W.t[key]
+        lc = cfg.latent_channels
+        x = ops.conv_direct(z_nhwc.reshape(n, h, w, lc), wq, bq, n=n, h=h, w=w, cin=lc, cout=lc, k=1, pad=(0, 0), out_f32=True)
+        wd, bd = W.conv_direct("decoder.conv_in")
+        c = cfg.block_out_channels[-1]
+        x = ops.conv_direct(x, wd, bd, n=n, h=h, w=w, cin=lc, cout=c, k=3)
+        x = FMap(x.reshape(n * h * w, c), n, h, w, c)
+        x = self._resnet("decoder.mid_block.resnets.0", x, c)
+        x = self._attention(x)
+        x = self._resnet("decoder.mid_block.resnets.1", x, c)
+        for _, resnets, up in self.blocks:
+            for p, _, cout in resnets:
+                x = self._resnet(p, x, cout)
+            if up:
+                u = ops.upsample_nearest(x.data, x.n, x.h, x.w, x.c, 2 * x.h, 2 * x.w)
+                wu, bu = W.conv(up)
+                out = ops.gemm_conv(u, wu, n_img=x.n, h_in=2 * x.h, w_in=2 * x.w, c0=x.c, lda0=x.c, n_out=x.c, taps=3, pad=1,
+                                    bias=bu)
+                x = FMap(out, x.n, 2 * x.h, 2 * x.w, x.c)
+        g, b = W.norm("decoder.conv_norm_out")
+        hn = ops.groupnorm(x.data, x.c, x.c, x.n, x.h * x.w, g, b, 1e-6, True, groups=cfg.norm_num_groups)
+        wn, bo = W.conv_n_padded("decoder.conv_out", self.COUT_PAD)
+        if to_unit_range:  # image / 2 + 0.5 in the epilogue: 0.5 * (acc + bias + 1)
+            if "decoder.conv_out.b01" not in W.t:
+                b01 = bo.clone()
+                b01[: cfg.out_channels] += 1.0
+                W.t["decoder.conv_out.b01"] = b01
+            bo = W.t["decoder.conv_out.b01"]
+        img = ops.gemm_conv(hn, wn, n_img=x.n, h_in=x.h, w_in=x.w, c0=x.c, lda0=x.c, n_out=self.COUT_PAD, taps=3, pad=1,
+                            bias=bo, out_f32=True, out_scale=0.5 if to_unit_range else 1.0)
+        img = img.reshape(x.n, x.h, x.w, self.COUT_PAD)[..., : cfg.out_channels]
+        return img.clamp(0, 1) if to_unit_range else img

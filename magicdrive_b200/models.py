@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import arch, ops
-from .engine import ControlNetEngine, UNetEngine
+from .engine import ControlNetEngine, UNetEngine, VaeDecoderEngine
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -376,3 +376,64 @@ class BEVControlNetModel(_B200Module):
         src = {k: v for k, v in unet.state_dict().items() if k in own and own[k].shape == v.shape}
         model.load_state_dict(src, strict=False)
         return model
+
+
+class DecoderOutput:  # diffusers/models/vae.py:27-36
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class AutoencoderKL(_B200Module):
+    """Decoder half of diffusers' AutoencoderKL (models/autoencoder_kl.py) for the pipeline's `decode_latents`
+    (pipeline_bev_controlnet.py:100-112): same constructor kwargs and checkpoint key names (`decoder.*`,
+    `post_quant_conv.*`; `encoder.*` / `quant_conv.*` of a full checkpoint are accepted and ignored), `.config.scaling_factor`
+    and `.config.block_out_channels` as the pipeline reads them (pipeline_controlnet.py:130-179), `decode(z).sample`.
+    Encoding is not on the path and raises."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        known, extra = _pick(arch.VaeConfig, dict(kwargs))
+        cfg = arch.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in known.items()})
+        if cfg.act_fn != "silu" or any(t != "UpDecoderBlock2D" for t in cfg.up_block_types):
+            raise ValueError("only the SD-1.5 AutoencoderKL layout (UpDecoderBlock2D, silu) is implemented")
+        self._init_common(cfg, arch.vae_decoder_param_shapes(cfg), extra)
+        self.training = False
+
+    _OLD_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}  # pre-0.17 checkpoint names
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = {}
+        for k, v in state_dict.items():
+            if k.startswith(("encoder.", "quant_conv.")):
+                continue
+            parts = k.split(".")
+            if "attentions" in parts and parts[-2] in self._OLD_ATTN:  # attention_processor.py:_from_deprecated_attn_block
+                k = ".".join(parts[:-2] + [self._OLD_ATTN[parts[-2]], parts[-1]])
+            sd[k] = v
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def engine(self) -> VaeDecoderEngine:
+        return self._get_engine(VaeDecoderEngine)
+
+    def encode(self, *a, **k):
+        raise NotImplementedError("AutoencoderKL.encode is not on the generation path (SURVEY.md §2.1); only decode is built")
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = True):
+        """z: (n, 4, h, w) latents already divided by scaling_factor, as the pipeline passes them -> (n, 3, 8h, 8w)."""
+        n, c, h, w = z.shape
+        z_nhwc = z.to(F32).permute(0, 2, 3, 1).contiguous().view(-1, c)
+        img = self.engine().decode(z_nhwc, n, h, w).permute(0, 3, 1, 2).to(z.dtype)
+        return DecoderOutput(img) if return_dict else (img,)
+
+    @torch.no_grad()
+    def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """StableDiffusionBEVControlNetPipeline.decode_latents (:100-112) on (b, n_cam, 4, h, w) latents, with the
+        1/scaling_factor, image/2+0.5 and clamp folded into the first and last convolution: (b, n_cam, 8h, 8w, 3) fp32."""
+        b, n_cam, c, h, w = latents.shape
+        z = latents.to(self.device, F32).permute(0, 1, 3, 4, 2).contiguous().view(-1, c)
+        img = self.engine().decode(z, b * n_cam, h, w, scale=1.0 / self.config["scaling_factor"], to_unit_range=True)
+        return img.reshape(b, n_cam, *img.shape[1:])

@@ -226,6 +226,17 @@ def layernorm(x, gamma, beta, eps=1e-5):
     return out
 
 
+def softmax_rows(s, cols: int, cols_out: int):
+    """fp32 scores [rows, >=cols] -> bf16 probabilities [rows, cols_out], columns >= cols zero."""
+    global _launches
+    _need_cuda(s)
+    out = torch.empty((s.shape[0], cols_out), dtype=BF16, device=s.device)
+    check(_lib.lib().mdb_softmax_rows(_ptr(s), s.stride(0), s.shape[0], cols, _ptr(out), cols_out, cols_out, _stream()),
+          "mdb_softmax_rows")
+    _launches += 1
+    return out
+
+
 def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=None, n_sets=1, out=None, b_kv=None):
     """q: [b*lq, >=heads*d] view with row stride ldq, k/v [b_kv*lk, ...] likewise; returns [b*lq, heads*d] bf16."""
     b_kv = b if b_kv is None else b_kv

@@ -63,7 +63,8 @@ def resnet_block(sd: SD, p: str, x, temb, groups=32, eps=1e-5):
     """ResnetBlock2D.forward, diffusers/models/resnet.py:590-640 (time_embedding_norm='default', scale 1)."""
     h = F.silu(F.group_norm(x, groups, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps))
     h = _conv(sd, p + ".conv1", h)
-    h = h + _lin(sd, p + ".time_emb_proj", F.silu(temb))[:, :, None, None]
+    if temb is not None:  # the VAE's ResnetBlock2D have temb_channels=None (vae.py:184)
+        h = h + _lin(sd, p + ".time_emb_proj", F.silu(temb))[:, :, None, None]
     h = F.silu(F.group_norm(h, groups, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], eps))
     h = _conv(sd, p + ".conv2", h)
     if (p + ".conv_shortcut.weight") in sd:
@@ -286,6 +287,40 @@ def controlnet_forward(sd: SD, cfg: arch.ControlNetConfig, sample, timestep, cam
 
 
 # ---------------------------------------------------------------------------------------------- scheduler + loop
+def vae_decode(sd: SD, cfg: "arch.VaeConfig", z):
+    """AutoencoderKL.decode (autoencoder_kl.py:177-196: post_quant_conv -> Decoder.forward, vae.py:226-273): conv_in,
+    UNetMidBlock2D (resnet, single-head attention with GroupNorm + residual, resnet; unet_2d_blocks.py:395-473 with the
+    Attention built at :433-446, processed by AttnProcessor2_0 attention_processor.py:1202-1272), 4 UpDecoderBlock2D
+    (3 resnets + nearest x2 + conv, unet_2d_blocks.py:2223-2290 / resnet.py:137-172), GroupNorm(1e-6), SiLU, conv_out."""
+    g, eps = cfg.norm_num_groups, 1e-6
+    x = _conv(sd, "post_quant_conv", z, padding=0)
+    x = _conv(sd, "decoder.conv_in", x)
+    x = resnet_block(sd, "decoder.mid_block.resnets.0", x, None, g, eps)
+    a = "decoder.mid_block.attentions.0"
+    b, c, h, w = x.shape
+    t = F.group_norm(x.view(b, c, h * w), g, sd[a + ".group_norm.weight"], sd[a + ".group_norm.bias"], eps).transpose(1, 2)
+    q, k, v = _lin(sd, a + ".to_q", t), _lin(sd, a + ".to_k", t), _lin(sd, a + ".to_v", t)
+    o = torch.softmax(q @ k.transpose(1, 2) * c ** -0.5, dim=-1) @ v
+    x = x + _lin(sd, a + ".to_out.0", o).transpose(1, 2).reshape(b, c, h, w)
+    x = resnet_block(sd, "decoder.mid_block.resnets.1", x, None, g, eps)
+    for _, resnets, up in arch.vae_decoder_blocks(cfg):
+        for p, _, _ in resnets:
+            x = resnet_block(sd, p, x, None, g, eps)
+        if up:
+            x = _conv(sd, up, F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    x = F.silu(F.group_norm(x, g, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], eps))
+    return _conv(sd, "decoder.conv_out", x)
+
+
+def decode_latents(sd: SD, cfg: "arch.VaeConfig", latents):
+    """StableDiffusionBEVControlNetPipeline.decode_latents (pipeline_bev_controlnet.py:100-112): (b, n_cam, 4, h, w)
+    latents -> (b, n_cam, 8h, 8w, 3) images in [0, 1]."""
+    b = latents.shape[0]
+    img = vae_decode(sd, cfg, (latents / cfg.scaling_factor).reshape(-1, *latents.shape[2:]))
+    img = (img / 2 + 0.5).clamp(0, 1)
+    return img.reshape(b, -1, *img.shape[1:]).permute(0, 1, 3, 4, 2)
+
+
 class DDIM:
     """DDIMScheduler (scaled_linear betas, clip_sample False, set_alpha_to_one False, steps_offset 1, eta 0):
     third_party/diffusers/src/diffusers/schedulers/scheduling_ddim.py:120-160 (init), 287-323 (set_timesteps,

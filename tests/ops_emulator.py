@@ -123,6 +123,11 @@ def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=No
     return res
 
 
+def softmax_rows(s, cols, cols_out):
+    p = torch.softmax(s[:, :cols].float(), -1)
+    return _act(F.pad(p, (0, cols_out - cols)))
+
+
 def add(a, b):
     return _act(a.float() + b.float())
 
@@ -216,7 +221,7 @@ class workspace_slot:
         return False
 
 
-EMULATED = ["gemm_conv", "linear", "conv_direct", "groupnorm", "layernorm", "attention", "add", "upsample_nearest",
+EMULATED = ["softmax_rows", "gemm_conv", "linear", "conv_direct", "groupnorm", "layernorm", "attention", "add", "upsample_nearest",
             "linear_small", "timestep_embedding", "fourier_embed", "nchw_to_nhwc", "nhwc_to_nchw", "f32_to_bf16",
             "pack_latents", "cfg_ddim_step", "cfg_unipc_step", "pin_views", "workspace_slot"]
 

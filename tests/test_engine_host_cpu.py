@@ -80,3 +80,33 @@ def test_denoiser_through_emulated_operators_matches_the_oracle_loop(emulated, s
     ref = O.denoise_loop(usd, csd, ucfg, ccfg, inp["latents"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
                          inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], 3, guidance, scheduler=scheduler)
     assert out.shape == ref.shape and rel_l2(out, ref) < 3e-3
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("h,w", [(10, 13), (7, 9)])
+def test_vae_decoder_through_emulated_operators_matches_the_oracle(emulated, h, w):
+    """VaeDecoderEngine host logic (post_quant folding, single-head attention as GEMM + row softmax + GEMM with padded
+    keys, x2 upsampling chain, unit-range epilogue) vs the oracle restatement of AutoencoderKL.decode."""
+    cfg = arch.VaeConfig(block_out_channels=(64, 128, 128, 128))
+    sd = _bf16_exact(arch.synthetic_state_dict(arch.vae_decoder_param_shapes(cfg), 51))
+    vae = models.AutoencoderKL(**asdict(cfg))
+    # a full AutoencoderKL checkpoint with pre-0.17 attention names loads too
+    full = dict(sd)
+    for new, old in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn")):
+        for leaf in ("weight", "bias"):
+            full[f"decoder.mid_block.attentions.0.{old}.{leaf}"] = full.pop(f"decoder.mid_block.attentions.0.{new}.{leaf}")
+    full["encoder.conv_in.weight"] = torch.zeros(64, 3, 3, 3)
+    full["quant_conv.weight"] = torch.zeros(8, 8, 1, 1)
+    vae.load_state_dict(full)
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn(3, 4, h, w, generator=g)
+    out = vae.decode(z).sample
+    ref = O.vae_decode(sd, cfg, z)
+    assert out.shape == ref.shape == (3, 3, 8 * h, 8 * w) and rel_l2(out, ref) < 1e-5
+    lat = torch.randn(1, 3, 4, h, w, generator=g) * 0.2
+    imgs = vae.decode_latents(lat)
+    ref_imgs = O.decode_latents(sd, cfg, lat)
+    assert imgs.shape == ref_imgs.shape == (1, 3, 8 * h, 8 * w, 3)
+    assert (imgs - ref_imgs).abs().max() < 1e-5 and 0.0 <= imgs.min() and imgs.max() <= 1.0
+    with pytest.raises(NotImplementedError):
+        vae.encode(z)

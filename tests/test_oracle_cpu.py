@@ -213,3 +213,33 @@ def test_oracle_reproduces_reference_given_view_fixture(case, scheduler, change)
                          scheduler=scheduler, conditional_latents=pinned_latents(p["pinned_seed"]), change_every_input=change)
     ref = p["outputs"][case]
     torch.testing.assert_close(out, ref, rtol=1e-3, atol=3e-4 * ref.abs().max().item())
+
+
+@torch.no_grad()
+def test_oracle_vae_decode_matches_reference_autoencoder():
+    """AutoencoderKL.decode of the reference's diffusers (autoencoder_kl.py:177-196) vs the restatement, same weights."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not mounted")
+    from magicdrive_b200 import arch
+    R = ref_shim.load()
+    cfg = arch.VaeConfig(block_out_channels=(32, 64, 64, 64))
+    vae = R.AutoencoderKL(block_out_channels=list(cfg.block_out_channels), down_block_types=["DownEncoderBlock2D"] * 4,
+                          up_block_types=["UpDecoderBlock2D"] * 4, latent_channels=4, layers_per_block=2)
+    shapes = arch.vae_decoder_param_shapes(cfg)
+    ref_sd = {k: tuple(v.shape) for k, v in vae.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    assert ref_sd == dict(shapes)
+    sd = arch.synthetic_state_dict(shapes, 5)
+    vae.load_state_dict(sd, strict=False)
+    z = torch.randn(2, 4, 10, 13, generator=torch.Generator().manual_seed(1))
+    torch.testing.assert_close(O.vae_decode(sd, cfg, z), vae.decode(z).sample, rtol=1e-4, atol=1e-4)
+    assert len(arch.vae_decoder_param_shapes(arch.VaeConfig())) == 140  # SD-1.5 VAE: decoder + post_quant tensors
+
+
+@torch.no_grad()
+def test_oracle_vae_decode_reproduces_reference_fixture():
+    from magicdrive_b200 import arch
+    g = golden("vae_decode.pt")
+    cfg = arch.VaeConfig(block_out_channels=tuple(g["block_out_channels"]))
+    sd = arch.synthetic_state_dict(arch.vae_decoder_param_shapes(cfg), g["seed"])
+    torch.testing.assert_close(O.vae_decode(sd, cfg, g["z"]), g["sample"], rtol=1e-4, atol=1e-4)
