@@ -133,13 +133,14 @@ class BEVControlNetDenoiser:
     prompt embeddings (the CLIP text encoder and the VAE sit outside the hot path: SURVEY.md §2.1)."""
 
     def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True,
-                 overlap_controlnet: bool = True, view_shard=None, scheduler: str = "ddim"):
+                 overlap_controlnet: bool = True, view_shard=None, scheduler: str = "ddim", vae=None):
         """view_shard: a dist.ViewShard to split the cameras of each scene across the ranks of its group (inputs are
         still passed with all n_cam views on every rank; the result is gathered back to (S, n_cam, ...)).
-        scheduler: "ddim" (eta = 0) or "unipc" (the reference's default sampler, misc/test_utils.py:129)."""
+        scheduler: "ddim" (eta = 0) or "unipc" (the reference's default sampler, misc/test_utils.py:129).
+        vae: a models.AutoencoderKL; enables output_type "pt" / "np" (decode_latents, pipeline_bev_controlnet.py:100-112)."""
         if scheduler not in ("ddim", "unipc"):
             raise ValueError(f"scheduler must be 'ddim' or 'unipc', got {scheduler!r}")
-        self.unet, self.controlnet = unet, controlnet
+        self.unet, self.controlnet, self.vae = unet, controlnet, vae
         self.overlap_controlnet = overlap_controlnet
         self.view_shard = view_shard
         unet.engine().set_view_shard(view_shard)
@@ -347,14 +348,20 @@ class BEVControlNetDenoiser:
                  conditional_latents_change_every_input: bool = True):
         """Same argument meaning as the reference pipeline call (:114-160); with `conditional_latents` it is the
         given-view pipeline's call (pipeline_bev_controlnet_given_view.py:36-37).  Returns latents (S, n_cam, 4, h, w) fp32."""
-        if output_type != "latent":
-            raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
+        if output_type not in ("latent", "pt", "np"):
+            raise ValueError(f"output_type must be 'latent', 'pt' or 'np', got {output_type!r}")
+        if output_type != "latent" and self.vae is None:
+            raise ValueError("output_type 'pt' / 'np' needs the denoiser to be built with vae=AutoencoderKL(...)")
         boxes = (bev_controlnet_kwargs or {}).get("bboxes_3d_data")
         st = self.prepare(latents, prompt_embeds, negative_prompt_embeds, camera_param, boxes, image, guidance_scale,
                           controlnet_conditioning_scale, conditional_latents, conditional_latents_change_every_input)
         self.set_schedule(st, num_inference_steps)
         self.run_steps(st, 0, num_inference_steps)
-        return self.latents_out(st)
+        latents = self.latents_out(st)
+        if output_type == "latent":
+            return latents
+        images = self.vae.decode_latents(latents)  # (S, n_cam, H, W, 3) in [0, 1]
+        return images.cpu().numpy() if output_type == "np" else images
 
     def latents_out(self, st):
         S, n_cam, h, w = st["S"], st["n_cam"], st["h"], st["w"]

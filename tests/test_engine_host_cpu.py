@@ -110,3 +110,24 @@ def test_vae_decoder_through_emulated_operators_matches_the_oracle(emulated, h, 
     assert (imgs - ref_imgs).abs().max() < 1e-5 and 0.0 <= imgs.min() and imgs.max() <= 1.0
     with pytest.raises(NotImplementedError):
         vae.encode(z)
+
+
+@torch.no_grad()
+def test_denoiser_decodes_images_when_given_a_vae(emulated):
+    ucfg, ccfg = tiny_configs()
+    un, cn, usd, csd = _modules(ucfg, ccfg, 41)
+    vcfg = arch.VaeConfig(block_out_channels=(64, 64, 64, 64))
+    vsd = _bf16_exact(arch.synthetic_state_dict(arch.vae_decoder_param_shapes(vcfg), 52))
+    vae = models.AutoencoderKL(**asdict(vcfg))
+    vae.load_state_dict(vsd)
+    inp = synthetic_inputs(1, 6, 10, 13, n_box=3, map_hw=52, seed=9)
+    kw = dict(image=inp["bev_map"], camera_param=inp["camera_param"], prompt_embeds=inp["prompt_embeds"],
+              negative_prompt_embeds=inp["negative_prompt_embeds"], latents=inp["latents"], num_inference_steps=2,
+              guidance_scale=2.0, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, vae=vae)
+    lat = pipe(**kw)
+    img = pipe(output_type="np", **kw)
+    ref = O.decode_latents(vsd, vcfg, lat)
+    assert img.shape == (1, 6, 80, 104, 3) and abs(img - ref.numpy()).max() < 1e-4
+    with pytest.raises(ValueError):
+        BEVControlNetDenoiser(un, cn, use_cuda_graph=False)(output_type="pt", **kw)
