@@ -12,8 +12,7 @@ import logging
 import os
 from collections import OrderedDict
 from dataclasses import asdict, dataclass, fields
-from types import SimpleNamespace
-from typing import Any, Dict, List, Optional, Tuple, Union
+from typing import Any, Dict, List, Tuple, Union
 
 import torch
 import torch.nn as nn

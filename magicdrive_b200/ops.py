@@ -6,7 +6,7 @@ Feature maps are NHWC bf16 ("channels innermost") everywhere; a token matrix [to
 """
 import ctypes as C
 import os
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 

@@ -11,7 +11,7 @@ Every function takes the reference's state-dict tensors by their checkpoint name
 it restates (paths relative to /root/reference).  Activations are NCHW like the reference.
 """
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

@@ -1,6 +1,5 @@
 """Shared test helpers (configs, golden loading, error metrics)."""
 import os
-from dataclasses import asdict
 
 import torch
 

@@ -11,7 +11,7 @@ from dataclasses import asdict
 import pytest
 import torch
 
-from magicdrive_b200 import arch, models, ops
+from magicdrive_b200 import models, ops
 from oracle import ref_shim
 from oracle import torch_oracle as O
 from tests.common import golden, tiny_configs, tiny_state_dicts

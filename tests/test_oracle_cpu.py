@@ -2,7 +2,6 @@
 (hard-coded slices copied from third_party/diffusers/tests/models/test_layers_utils.py and tests/schedulers), rebuilt
 here by replaying the reference constructors' RNG order with plain torch.nn layers; (b) fixtures produced by running
 the reference itself (tests/golden/*.pt <- oracle/make_golden.py)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn as nn
