@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run ControlNet and UNet encoder on one stream")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--scheduler", default="ddim", choices=["ddim", "unipc"],
+                    help="sampler fused into the step: ddim (BASELINE.json configs: 50-step DDIM) or unipc (the reference's default)")
+    ap.add_argument("--decode", action="store_true",
+                    help="also time the VAE decode of the scene's 6 views (SURVEY.md §8 f2) and report it as vae_decode")
     ap.add_argument("--shard", default="scenes", choices=["scenes", "views"],
                     help="N>1: scenes = independent scenes per GPU (default, weak scaling, no data-path collective); "
                          "views = the 6 cameras of the SAME scenes split across GPUs with an NCCL all-gather of the "
@@ -195,7 +199,8 @@ def main():
         shard = ViewShard(rank, world, 6)
         config["sharding"] = f"views: {6 // world} cameras per GPU, NCCL all-gather of cross-view K/V in each of the 16 multiview blocks"
     pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph, overlap_controlnet=not args.no_overlap,
-                                 view_shard=shard)
+                                 view_shard=shard, scheduler=args.scheduler)
+    config["scheduler"] = args.scheduler
     inp, h, w = make_inputs(args, 0 if by_views else rank)
     job_scenes = args.scenes if by_views else n_gpus * args.scenes  # scenes the whole job advances per step
     views_local = 6 // world if by_views else 6
@@ -339,6 +344,22 @@ def main():
                                "frac": TFLOP_PER_SCENE_STEP_CFG[args.res] * args.scenes * views_local / 6 / (ms_step * 1e-3) / peak_tf,
                                "note": "per GPU"}}
 
+    vae_decode = None
+    if args.decode:
+        from magicdrive_b200.models import AutoencoderKL
+        vae = AutoencoderKL(**asdict(arch.VaeConfig())).reset_parameters_synthetic(13).to(dev, torch.bfloat16)
+        lat5 = pipe.latents_out(st) * 0.18215
+        for _ in range(2):
+            vae.decode_latents(lat5)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            vae.decode_latents(lat5)
+        e1.record()
+        barrier()
+        vae_decode = {"ms_per_scene": e0.elapsed_time(e1) / 5 / args.scenes, "views": 6,
+                      "note": "AutoencoderKL.decode_latents of the 6 views at full resolution, eager launches, SD-1.5 VAE config, random-init weights"}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and n_gpus == 1:
@@ -361,6 +382,8 @@ def main():
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu, "cuda_graph": not args.no_graph,
                 "two_stream_overlap": not args.no_overlap}
+        if vae_decode is not None:
+            line["vae_decode"] = vae_decode
         print(json.dumps(line))
     if world > 1:
         from magicdrive_b200.dist import shutdown

@@ -153,3 +153,29 @@ def test_prepare_initialises_class_tokens_like_the_reference():
     cn2.reset_parameters_synthetic(1)
     cn2.prepare(cfg, tokenizer=None, text_encoder=None)
     assert torch.equal(cn2.bbox_embedder._class_tokens, before)
+
+
+def test_unsupported_configurations_raise_like_the_reference_would():
+    """Bad / unbuilt configurations are Python exceptions at construction or call time, never a silent different result
+    (errors = ValueError for bad config, unet_2d_condition_multiview.py:413-416)."""
+    from magicdrive_b200 import arch, models
+    from magicdrive_b200.dist import ViewShard
+    from magicdrive_b200.pipeline import BEVControlNetDenoiser, UniPCSchedule
+    ucfg, ccfg = tiny_configs()
+    with pytest.raises(ValueError):
+        models.BEVControlNetModel(**asdict(ccfg), bbox_embedder_param=dict(mode="owhr"))
+    with pytest.raises(ValueError):
+        models.BEVControlNetModel(**asdict(ccfg), map_embedder_cls="my.module.Cls")
+    with pytest.raises(ValueError):
+        models.AutoencoderKL(act_fn="gelu")
+    with pytest.raises(ValueError):
+        ViewShard(0, 4, 6)  # 6 cameras do not split over 4 ranks
+    with pytest.raises(ValueError):
+        UniPCSchedule(solver_order=3)
+    un, cn = models.UNet2DConditionModelMultiview(**asdict(ucfg)), models.BEVControlNetModel(**asdict(ccfg))
+    with pytest.raises(ValueError):
+        BEVControlNetDenoiser(un, cn, scheduler="pndm")
+    # CPU tensors: no fallback, a clear error instead
+    with pytest.raises(Exception) as ei:
+        un(torch.zeros(6, 4, 10, 13), 10, encoder_hidden_states=torch.zeros(6, 78, 768))
+    assert "CUDA" in str(ei.value)
