@@ -210,7 +210,7 @@ def test_attention_growing_scores(cuda_lib, monkeypatch, d, heads, lq, lk, kerne
 
 
 @pytest.mark.parametrize("kernel", ATTN_KERNELS)
-@pytest.mark.parametrize("l,heads,d", [(350, 8, 80), (1400, 8, 40), (91, 8, 160)])
+@pytest.mark.parametrize("l,heads,d", [(350, 8, 80), (1400, 8, 40), (91, 8, 160), (130, 2, 32), (130, 2, 64), (35, 2, 64)])
 def test_attention_two_sets_cross_view(cuda_lib, monkeypatch, kernel, l, heads, d):
     """attn4 'add' mode: out[view i] = attn(q_i, kv_left(i)) + attn(q_i, kv_right(i)) (blocks.py:112-121,213-217)."""
     _pick_attention_kernel(monkeypatch, kernel)
