@@ -179,3 +179,34 @@ def test_unsupported_configurations_raise_like_the_reference_would():
     with pytest.raises(Exception) as ei:
         un(torch.zeros(6, 4, 10, 13), 10, encoder_hidden_states=torch.zeros(6, 78, 768))
     assert "CUDA" in str(ei.value)
+
+
+@pytest.mark.parametrize("fmt", ["safetensors", "bin"])
+def test_from_pretrained_reads_diffusers_save_pretrained_directories(tmp_path, fmt):
+    """config.json + diffusion_pytorch_model.{safetensors,bin} as written by ModelMixin.save_pretrained
+    (multiview_runner.py:233-242): constructor kwargs incl. diffusers' private '_class_name' keys, dtype cast."""
+    import json
+
+    from magicdrive_b200 import arch, models
+    ucfg, ccfg = tiny_configs()
+    vcfg = arch.VaeConfig(block_out_channels=(64, 64, 64, 64))
+    cases = [("unet", models.UNet2DConditionModelMultiview, asdict(ucfg), arch.unet_param_shapes(ucfg)),
+             ("controlnet", models.BEVControlNetModel, asdict(ccfg), arch.controlnet_param_shapes(ccfg)),
+             ("vae", models.AutoencoderKL, asdict(vcfg), arch.vae_decoder_param_shapes(vcfg))]
+    for sub, cls, cfg, shapes in cases:
+        d = tmp_path / sub
+        d.mkdir()
+        sd = arch.synthetic_state_dict(shapes, 3)
+        (d / "config.json").write_text(json.dumps({"_class_name": cls.__name__, "_diffusers_version": "0.17.1",
+                                                   **{k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}}))
+        if fmt == "safetensors":
+            from safetensors.torch import save_file
+            save_file({k: v.contiguous() for k, v in sd.items()}, str(d / "diffusion_pytorch_model.safetensors"))
+        else:
+            torch.save(sd, d / "diffusion_pytorch_model.bin")
+        m = cls.from_pretrained(str(tmp_path), subfolder=sub, torch_dtype=torch.bfloat16)
+        got = m.state_dict()
+        assert set(got) == set(sd) and m.dtype == torch.bfloat16
+        for k in sd:
+            if sd[k].is_floating_point():
+                assert torch.equal(got[k], sd[k].to(torch.bfloat16)), k
