@@ -7,6 +7,10 @@ Differences from the reference that do not change results: latents stay fp32 and
 combine; `timestep` and the two DDIM coefficients are read from device memory so the captured graph is replayed
 unchanged for every step.  The reference refuses DDIM only because `scheduler.step` accepts a `generator`
 (:93-97); eta = 0 is deterministic, so no generator is needed.
+
+Also here: the reference's default sampler (UniPC, `scheduler="unipc"`), the given-view pipeline's per-step pinning of
+conditional views (pipeline_bev_controlnet_given_view.py), view-sharded execution over several GPUs (dist.ViewShard) and
+the optional VAE decode of the result (`vae=`, output_type "pt" / "np").
 """
 from typing import Dict, Optional
 
