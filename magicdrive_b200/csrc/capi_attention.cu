@@ -17,6 +17,7 @@
 #include <string.h>
 #include "attention_tc.cuh"
 #include "attention_tc2.cuh"
+#include "attention_tc3.cuh"
 
 namespace {
 
@@ -345,13 +346,48 @@ int launch_attention_tc2(const void* q, int ldq, const void* k, int ldk, const v
   return MDB_OK;
 }
 
-// Which kernel generation serves a call: MDB_ATTN_KERNEL = tc2 | tc | legacy (A/B switch, read per call).
-enum class AttnKernel { kLegacy, kTc, kTc2, kTc2Double };
+// Persistent form (attention_tc3.cuh), head dim <= 64; opt-in until it has been run on a GPU.
+template <int D>
+int launch_attention_tc3(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
+                         int heads, int lq, int lk, int b_kv, const int* kv_index, int n_sets, float scale, cudaStream_t st) {
+  using Cfg = mdb::AttnTc3Cfg<D>;
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mdb::attention_tc3_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc3 smem attr: %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  CUtensorMap tq, tk, tv;
+  if (!make_qkv_map(&tq, q, D, heads, lq, b, ldq) || !make_qkv_map(&tk, k, D, heads, lk, b_kv, ldk) ||
+      !make_qkv_map(&tv, v, D, heads, lk, b_kv, ldv))
+    return mdb::set_error(MDB_ERR_CUDA, "mdb_attention: cuTensorMapEncodeTiled failed (d=%d heads=%d lq=%d lk=%d)", D, heads,
+                          lq, lk);
+  mdb::AttnTc3Params p;
+  p.a.out = static_cast<__nv_bfloat16*>(out);
+  p.a.ldo = ldo, p.a.lq = lq, p.a.lk = lk, p.a.kv_index = kv_index, p.a.n_sets = n_sets;
+  p.a.scale_log2 = scale * 1.4426950408889634f;
+  p.n_qtiles = (lq + mdb::ATT_BM - 1) / mdb::ATT_BM, p.heads = heads, p.batch = b;
+  const long long items = static_cast<long long>(p.n_qtiles) * heads * b;
+  const int grid = static_cast<int>(items < 2LL * sms ? items : 2LL * sms);
+  cudaError_t le = mdb::launch_pdl(mdb::attention_tc3_kernel<D>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tq, tk, tv, p);
+  if (le != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc3_kernel launch: %s", cudaGetErrorString(le));
+  MDB_CHECK_LAUNCH("attention_tc3_kernel");
+  return MDB_OK;
+}
+
+// Which kernel generation serves a call: MDB_ATTN_KERNEL = tc3 | tc2 | tc2d | tc | legacy (A/B switch, read per call).
+enum class AttnKernel { kLegacy, kTc, kTc2, kTc2Double, kTc3 };
 AttnKernel attention_kernel_choice() {
   const char* legacy = getenv("MDB_ATTN_LEGACY");
   if (legacy && legacy[0] == '1') return AttnKernel::kLegacy;
   const char* e = getenv("MDB_ATTN_KERNEL");
   if (e && !strcmp(e, "legacy")) return AttnKernel::kLegacy;
+  if (e && !strcmp(e, "tc3")) return AttnKernel::kTc3;
   if (e && !strcmp(e, "tc2")) return AttnKernel::kTc2;
   if (e && !strcmp(e, "tc2d")) return AttnKernel::kTc2Double;
   if (e && !strcmp(e, "tc")) return AttnKernel::kTc;
@@ -372,9 +408,17 @@ extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, con
   if (!kv_index && b_kv != b) return set_error(MDB_ERR_INVALID, "mdb_attention: b_kv != b needs kv_index");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const AttnKernel which = attention_kernel_choice();
+  if (which == AttnKernel::kTc3 && scale > 0.f) {  // persistent variant (opt-in); other head dims fall through to tc2
+    switch (d) {
+      case 40: return launch_attention_tc3<40>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      case 32: return launch_attention_tc3<32>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      case 64: return launch_attention_tc3<64>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st);
+      default: break;
+    }
+  }
 #define MDB_TC2(DD, DBL) \
   return launch_attention_tc2<DD, DBL>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, b_kv, kv_index, n_sets, scale, st)
-  if ((which == AttnKernel::kTc2 || which == AttnKernel::kTc2Double) && scale > 0.f) {
+  if ((which == AttnKernel::kTc2 || which == AttnKernel::kTc2Double || which == AttnKernel::kTc3) && scale > 0.f) {
     const bool dbl = which == AttnKernel::kTc2Double;  // tc2: two CTAs/SM with one S buffer where d <= 64
     switch (d) {
       case 40: if (dbl) MDB_TC2(40, true); else MDB_TC2(40, false);

@@ -1,7 +1,8 @@
 """Opt-in GPU tests of kernel variants that were written but not yet measured / validated on a GPU (so the driver's
 `pytest -m gpu` does not depend on them):  MDB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_zzz_experimental_gpu.py -m gpu
   * gn_cluster_kernel (MDB_GN_CLUSTER=1): pixel-major GroupNorm on a thread-block cluster per image (capi_norm.cu).
-A/B timing: tools/bench_norm.py."""
+  * attention_tc3_kernel (MDB_ATTN_KERNEL=tc3): persistent form of attention_tc2 (attention_tc3.cuh).
+A/B timing: tools/bench_norm.py, tools/bench_attn.py tc3 tc2 tc."""
 import os
 
 import pytest
@@ -45,3 +46,22 @@ def test_groupnorm_cluster_variant(cuda_lib, monkeypatch, c0, c1, hw, n, silu):
     assert (out.float() - ref).abs().max().item() < 0.06
     assert ((out.float() - ref).norm() / ref.norm()).item() < 8e-3
     assert (out.float() - base.float()).abs().max().item() < 0.04  # both round the same fp32 values to bf16
+
+
+@pytest.mark.parametrize("d,heads", [(40, 8), (32, 2), (64, 2)])
+@pytest.mark.parametrize("lq,lk", [(1400, 1400), (350, 98), (91, 91), (28, 28), (70, 130), (130, 257), (200, 40), (129, 600)])
+def test_attention_persistent_variant(cuda_lib, monkeypatch, d, heads, lq, lk):
+    from tests.test_kernels_gpu import test_attention
+    test_attention(cuda_lib, monkeypatch, d, heads, lq, lk, "tc3")
+
+
+@pytest.mark.parametrize("d,heads,lq,lk", [(40, 8, 300, 700), (40, 8, 1400, 1400)])
+def test_attention_persistent_variant_growing_scores(cuda_lib, monkeypatch, d, heads, lq, lk):
+    from tests.test_kernels_gpu import test_attention_growing_scores
+    test_attention_growing_scores(cuda_lib, monkeypatch, d, heads, lq, lk, "tc3")
+
+
+@pytest.mark.parametrize("l,heads,d", [(1400, 8, 40), (130, 2, 32), (130, 2, 64), (35, 2, 64)])
+def test_attention_persistent_variant_two_sets(cuda_lib, monkeypatch, l, heads, d):
+    from tests.test_kernels_gpu import test_attention_two_sets_cross_view
+    test_attention_two_sets_cross_view(cuda_lib, monkeypatch, "tc3", l, heads, d)
