@@ -18,7 +18,7 @@ for row in r:
     agg[name][0] += 1
     agg[name][1] += v
     tot += v
-print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.3f} ms summed device time (cold-cache, serialised)")
+print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.3f} ms summed device time (serialised launches; cache state as captured: see profiles/README.md)")
 print("#   time_us  share  launches  avg_us  kernel")
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     print(f"{t:10.1f} {100 * t / tot:5.1f}% {n:5d} {t / n:8.1f}  {k[:110]}")
