@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--scheduler", default="ddim", choices=["ddim", "unipc"],
                     help="sampler fused into the step: ddim (BASELINE.json configs: 50-step DDIM) or unipc (the reference's default)")
+    ap.add_argument("--cfg-streams", action="store_true",
+                    help="opt-in: run the unconditional / conditional guidance halves as two concurrent graph branches")
     ap.add_argument("--decode", action="store_true",
                     help="also time the VAE decode of the scene's 6 views (SURVEY.md §8 f2) and report it as vae_decode")
     ap.add_argument("--shard", default="scenes", choices=["scenes", "views"],
@@ -199,8 +201,10 @@ def main():
         shard = ViewShard(rank, world, 6)
         config["sharding"] = f"views: {6 // world} cameras per GPU, NCCL all-gather of cross-view K/V in each of the 16 multiview blocks"
     pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph, overlap_controlnet=not args.no_overlap,
-                                 view_shard=shard, scheduler=args.scheduler)
+                                 view_shard=shard, scheduler=args.scheduler, cfg_streams=args.cfg_streams)
     config["scheduler"] = args.scheduler
+    if args.cfg_streams:
+        config["cfg_streams"] = True
     inp, h, w = make_inputs(args, 0 if by_views else rank)
     job_scenes = args.scenes if by_views else n_gpus * args.scenes  # scenes the whole job advances per step
     views_local = 6 // world if by_views else 6

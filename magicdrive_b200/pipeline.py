@@ -137,15 +137,20 @@ class BEVControlNetDenoiser:
     prompt embeddings (the CLIP text encoder and the VAE sit outside the hot path: SURVEY.md §2.1)."""
 
     def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True,
-                 overlap_controlnet: bool = True, view_shard=None, scheduler: str = "ddim", vae=None):
+                 overlap_controlnet: bool = True, view_shard=None, scheduler: str = "ddim", vae=None,
+                 cfg_streams: bool = False):
         """view_shard: a dist.ViewShard to split the cameras of each scene across the ranks of its group (inputs are
         still passed with all n_cam views on every rank; the result is gathered back to (S, n_cam, ...)).
         scheduler: "ddim" (eta = 0) or "unipc" (the reference's default sampler, misc/test_utils.py:129).
-        vae: a models.AutoencoderKL; enables output_type "pt" / "np" (decode_latents, pipeline_bev_controlnet.py:100-112)."""
+        vae: a models.AutoencoderKL; enables output_type "pt" / "np" (decode_latents, pipeline_bev_controlnet.py:100-112).
+        cfg_streams (opt-in, not yet measured): run the unconditional and the conditional half of the guidance batch as
+        two concurrent branches (ControlNet -> UNet each) instead of ControlNet || UNet-encoder on the whole batch, so
+        every kernel's fixed cost is overlapped by the other half's kernels; same arithmetic per sample."""
         if scheduler not in ("ddim", "unipc"):
             raise ValueError(f"scheduler must be 'ddim' or 'unipc', got {scheduler!r}")
         self.unet, self.controlnet, self.vae = unet, controlnet, vae
         self.overlap_controlnet = overlap_controlnet
+        self.cfg_streams = cfg_streams
         self.view_shard = view_shard
         unet.engine().set_view_shard(view_shard)
         self._side = {}
@@ -177,6 +182,61 @@ class BEVControlNetDenoiser:
         if pin is not None and pin["mode"] == "change":
             # given views are re-noised from their clean latents at every step (pipeline_bev_controlnet_given_view.py:283-296)
             ops.pin_views(lat, pin["cond"], pin["noise0"], pin["coef_dev"], pin["mask"], h * w, c=lat.shape[1])
+        if self.cfg_streams and st["cfg"] and st.get("u_temb") is not None:
+            eps = self._step_models_cfg_streams(st, lat)
+        else:
+            eps = self._step_models(st, lat)
+        if pin is not None and pin["mode"] == "once":
+            # given views follow their own initial noise instead of the prediction (:379-389): overwrite both guidance
+            # halves, so the combine u + s (c - u) returns exactly that noise
+            npix = lat.shape[0]
+            for half in range(2 if st["cfg"] else 1):
+                ops.pin_views(eps[half * npix:(half + 1) * npix], None, pin["noise0"], pin["one"], pin["mask"], h * w,
+                              c=lat.shape[1])
+        if self.scheduler_name == "ddim":
+            ops.cfg_ddim_step(eps, lat, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
+        else:
+            last, m0, m1 = st["hist"]
+            ops.cfg_unipc_step(eps, lat, last, m0, m1, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
+
+    def _step_models_cfg_streams(self, st, lat):
+        """[uncond | cond] halves as two concurrent branches; returns eps fp32 [V*h*w, 8] (uncond rows first)."""
+        ue, ce = st["ue"], st["ce"]
+        V, h, w, lc = st["V"], st["h"], st["w"], st["lc"]
+        vh, npix = V // 2, lat.shape[0]
+        x = ops.pack_latents(lat, ue.CIN_PAD, repeat=1)  # both halves read the same latents (:352-354)
+        if "eps_buf" not in st:
+            st["eps_buf"] = torch.zeros((2 * npix, ue.COUT_PAD), dtype=F32, device=lat.device)
+        eps = st["eps_buf"]
+        on_gpu = lat.is_cuda
+        main = torch.cuda.current_stream() if on_gpu else None
+        side = self._side_stream(lat.device) if on_gpu else None
+        if on_gpu:
+            side.wait_stream(main)
+        for half in (1, 0):  # the side branch is enqueued first, the main branch runs while it executes
+            rows = slice(half * vh * lc, (half + 1) * vh * lc)
+            views = slice(half * vh, (half + 1) * vh)
+            c_kv = {k: v[rows] for k, v in st["c_kv"].items()}
+            u_kv = {k: v[rows] for k, v in st["u_kv"].items()}
+
+            def branch():
+                down, mid, _, _ = ce.forward(x, vh, h, w, st["t_dev"][views], c_kv, lc, st["map"][views], st["cond_scale"],
+                                             temb_all=st["c_temb"])
+                e = ue.forward(x, vh, h, w, st["t_dev"][views], u_kv, lc, down, mid, temb_all=st["u_temb"])
+                eps[half * npix:(half + 1) * npix].copy_(e)
+            if on_gpu and half == 1:
+                with torch.cuda.stream(side), ops.workspace_slot(1):
+                    branch()
+            else:
+                branch()
+        if on_gpu:
+            main.wait_stream(side)
+        return eps
+
+    def _step_models(self, st, lat):
+        """ControlNet + UNet on the whole guidance batch; returns eps fp32 [V*h*w, 8]."""
+        ue, ce = st["ue"], st["ce"]
+        V, h, w = st["V"], st["h"], st["w"]
         # bf16, channel-padded to one K block; CFG: [uncond ; cond] share the latents (:352-354) -> repeat = 2
         x = ops.pack_latents(lat, ue.CIN_PAD, repeat=2 if st["cfg"] else 1)
         if self.overlap_controlnet and st.get("u_temb") is not None:
@@ -196,18 +256,7 @@ class BEVControlNetDenoiser:
             down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
                                          temb_all=st.get("c_temb"))
             eps = ue.forward(x, V, h, w, st["t_dev"], st["u_kv"], st["lc"], down, mid, temb_all=st.get("u_temb"))
-        if pin is not None and pin["mode"] == "once":
-            # given views follow their own initial noise instead of the prediction (:379-389): overwrite both guidance
-            # halves, so the combine u + s (c - u) returns exactly that noise
-            npix = lat.shape[0]
-            for half in range(2 if st["cfg"] else 1):
-                ops.pin_views(eps[half * npix:(half + 1) * npix], None, pin["noise0"], pin["one"], pin["mask"], h * w,
-                              c=lat.shape[1])
-        if self.scheduler_name == "ddim":
-            ops.cfg_ddim_step(eps, lat, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
-        else:
-            last, m0, m1 = st["hist"]
-            ops.cfg_unipc_step(eps, lat, last, m0, m1, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
+        return eps
 
     @torch.no_grad()
     def prepare(self, latents, prompt_embeds, negative_prompt_embeds, camera_param, bboxes_3d_data, image,

@@ -131,3 +131,20 @@ def test_denoiser_decodes_images_when_given_a_vae(emulated):
     assert img.shape == (1, 6, 80, 104, 3) and abs(img - ref.numpy()).max() < 1e-4
     with pytest.raises(ValueError):
         BEVControlNetDenoiser(un, cn, use_cuda_graph=False)(output_type="pt", **kw)
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("scheduler", ["ddim", "unipc"])
+def test_cfg_streams_mode_computes_the_same_step(emulated, scheduler):
+    """The opt-in guidance-half branches (BEVControlNetDenoiser(cfg_streams=True)) slice the hoisted conditioning per half
+    and must reproduce the batched step; here on CPU, where the two branches run one after the other."""
+    ucfg, ccfg = tiny_configs()
+    un, cn, usd, csd = _modules(ucfg, ccfg, 41)
+    inp = synthetic_inputs(2, 6, 10, 13, n_box=3, map_hw=52, seed=9)
+    kw = dict(image=inp["bev_map"], camera_param=inp["camera_param"], prompt_embeds=inp["prompt_embeds"],
+              negative_prompt_embeds=inp["negative_prompt_embeds"], latents=inp["latents"], num_inference_steps=3,
+              guidance_scale=2.0, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
+    base = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, scheduler=scheduler)(**kw)
+    split = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, scheduler=scheduler,
+                                  cfg_streams=True)(**kw)
+    assert rel_l2(split, base) < 1e-5

@@ -14,5 +14,7 @@ for v in "" "MDB_ATTN_KERNEL=tc3" "MDB_GN_CLUSTER=1" "MDB_ATTN_KERNEL=tc3 MDB_GN
   echo "== $v" >> gpurun_out/bench_variants.log
   env $v timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ms/step', d['ms_per_step'], 'scene-steps/s', d['value'])" >> gpurun_out/bench_variants.log 2>&1
 done
+echo "== --cfg-streams" >> gpurun_out/bench_variants.log
+timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --cfg-streams 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ms/step', d['ms_per_step'], 'scene-steps/s', d['value'])" >> gpurun_out/bench_variants.log 2>&1
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --scheduler unipc --decode 2>/dev/null | tail -1 > gpurun_out/bench_unipc_decode.json
 tail -n +1 gpurun_out/zz_tests.log gpurun_out/experimental_tests.log gpurun_out/bench_attn_tc3.log gpurun_out/bench_norm.log gpurun_out/bench_variants.log
