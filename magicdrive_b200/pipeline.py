@@ -175,8 +175,7 @@ class BEVControlNetDenoiser:
 
     # ------------------------------------------------------------------ one step on resident buffers
     def _step(self, st):
-        ue, ce = st["ue"], st["ce"]
-        V, h, w = st["V"], st["h"], st["w"]
+        h, w = st["h"], st["w"]
         lat = st["latents"]  # fp32 [S*ncam*h*w, 4] NHWC, S scenes (no CFG duplication)
         pin = st.get("pin")
         if pin is not None and pin["mode"] == "change":
