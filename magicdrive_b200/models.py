@@ -242,7 +242,18 @@ class BEVControlNetModel(_B200Module):
         if extra.get("map_embedder_cls") not in (None,):
             raise ValueError("custom map_embedder_cls is not implemented (BEVControlNetConditioningEmbedding only)")
         self._init_common(cfg, arch.controlnet_param_shapes(cfg), extra)
-        self.uncond_map = None
+        # unconditional BEV map (unet_addon_rawbox.py:188-202): present (and a checkpoint key) only when configured
+        um = extra.get("use_uncond_map")
+        if um is not None and extra.get("drop_cond_ratio", 0.0) > 0:
+            if um not in ("negative1", "random", "learnable"):
+                raise TypeError(f"Unknown map type: {um}.")
+            t = -torch.ones(tuple(cfg.map_size)) if um == "negative1" else torch.randn(tuple(cfg.map_size))
+            if um == "learnable":
+                self.register_parameter("uncond_map", nn.Parameter(t, requires_grad=False))
+            else:
+                self.register_buffer("uncond_map", t)
+        else:
+            self.uncond_map = None
         self.training = False
 
     def engine(self) -> ControlNetEngine:
@@ -286,7 +297,8 @@ class BEVControlNetModel(_B200Module):
                     pad = torch.zeros_like(v[:, :, :1]).expand(-1, -1, token_num, *v.shape[3:])
                     v = torch.cat([v, pad], dim=2)
                 ret["bboxes_3d_data"][key] = v
-        ret["image"] = image
+        # the unconditional half sees the configured uncond map instead of the scene's (substitute_with_uncond_map, :378-395)
+        ret["image"] = image if self.uncond_map is None else self.uncond_map[None].expand_as(image).to(image).clone()
         for k, v in kwargs.items():
             ret[k] = v
         return ret

@@ -89,7 +89,7 @@ def load():
     return out
 
 
-def build_reference_models(ucfg, ccfg, img_size=(224, 400)):
+def build_reference_models(ucfg, ccfg, img_size=(224, 400), **controlnet_kwargs):
     """Instantiate the reference UNet2DConditionModelMultiview + BEVControlNetModel for our config dataclasses."""
     R = load()
     base = R.UNet2DConditionModel(
@@ -108,5 +108,5 @@ def build_reference_models(ucfg, ccfg, img_size=(224, 400)):
         bbox_embedder_param=dict(n_classes=ccfg.bbox_n_classes, class_token_dim=ccfg.bbox_class_token_dim,
                                  trainable_class_token=False, use_text_encoder_init=False,
                                  embedder_num_freq=ccfg.bbox_num_freqs, proj_dims=list(ccfg.bbox_proj_dims),
-                                 mode="all-xyz", minmax_normalize=False))
+                                 mode="all-xyz", minmax_normalize=False), **controlnet_kwargs)
     return mv.eval(), cn.eval()

@@ -462,7 +462,7 @@ def add_uncond_to_kwargs(sd: SD, ccfg, camera_param, bboxes_3d_data):
 
 def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_prompt_embeds, camera_param,
                  bboxes_3d_data, bev_map, num_inference_steps, guidance_scale, return_all=False, scheduler="ddim",
-                 conditional_latents=None, change_every_input=True):
+                 conditional_latents=None, change_every_input=True, use_zero_map_as_unconditional=False):
     """StableDiffusionBEVControlNetPipeline.__call__ steps 5-8 (magicdrive/pipeline/pipeline_bev_controlnet.py:
     303-451) with DDIM eta=0 and output_type='latent'.  latents: (b, 4, h, w) initial noise (shared by the views,
     :326).  Returns (b, n_cam, 4, h, w).
@@ -476,7 +476,12 @@ def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_
     cfg_on = guidance_scale > 1.0
     lat = torch.stack([latents] * n_cam, dim=1)
     text = torch.cat([negative_prompt_embeds, prompt_embeds]) if cfg_on else prompt_embeds
-    image = torch.cat([bev_map, bev_map]) if cfg_on else bev_map
+    # unconditional map: the scene's, zeros (:296-300), or the ControlNet's `uncond_map` buffer when the checkpoint has
+    # one (add_uncond_to_kwargs -> substitute_with_uncond_map, unet_addon_rawbox.py:378-395, 676-679)
+    un_map = torch.zeros_like(bev_map) if use_zero_map_as_unconditional else bev_map
+    if "uncond_map" in csd:
+        un_map = csd["uncond_map"][None].expand_as(bev_map).to(bev_map)
+    image = torch.cat([un_map, bev_map]) if cfg_on else bev_map
     cam, boxes = (add_uncond_to_kwargs(csd, ccfg, camera_param, bboxes_3d_data) if cfg_on
                   else (camera_param, bboxes_3d_data))
     hist = []

@@ -115,3 +115,31 @@ def test_denoiser_host_logic_reproduces_reference_given_view_pipeline(cpu_standi
     if plain["steps"] == p["steps"]:
         out = _call(pipe, inp, plain["steps"], plain["guidance"])
         torch.testing.assert_close(out, plain["latents_out"], rtol=1e-3, atol=3e-4 * plain["latents_out"].abs().max().item())
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("case", ["zero_map", "negative1"])
+def test_unconditional_map_options_reproduce_the_reference(cpu_standins, case):
+    """use_zero_map_as_unconditional (pipeline_bev_controlnet.py:296-300) and a ControlNet configured with
+    use_uncond_map='negative1' (unet_addon_rawbox.py:188-202, 676-679), fixtures from the reference pipeline."""
+    from oracle import torch_oracle as O
+    p = golden("tiny_uncond_map.pt")
+    inp = golden(p["inputs_from"])["inputs"]
+    ucfg, ccfg = tiny_configs()
+    usd, csd = tiny_state_dicts(p["seed"])
+    un = models.UNet2DConditionModelMultiview(**asdict(ucfg))
+    extra = dict(use_uncond_map="negative1", drop_cond_ratio=0.25) if case == "negative1" else {}
+    cn = models.BEVControlNetModel(**asdict(ccfg), **extra)
+    un.load_state_dict(usd)
+    if case == "negative1":
+        assert "uncond_map" in cn.state_dict() and torch.all(cn.uncond_map == -1)
+        csd = dict(csd, uncond_map=cn.uncond_map.clone())
+    cn.load_state_dict(csd)
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False)
+    out = _call(pipe, inp, p["steps"], p["guidance"], use_zero_map_as_unconditional=(case == "zero_map"))
+    ref = p["outputs"][case]
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=3e-4 * ref.abs().max().item())
+    orc = O.denoise_loop(usd, csd, ucfg, ccfg, inp["latents"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                         inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], p["steps"], p["guidance"],
+                         use_zero_map_as_unconditional=(case == "zero_map"))
+    torch.testing.assert_close(orc, ref, rtol=1e-3, atol=3e-4 * ref.abs().max().item())
