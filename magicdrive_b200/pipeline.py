@@ -260,7 +260,7 @@ class BEVControlNetDenoiser:
     @torch.no_grad()
     def prepare(self, latents, prompt_embeds, negative_prompt_embeds, camera_param, bboxes_3d_data, image,
                 guidance_scale=2.0, controlnet_conditioning_scale=1.0, conditional_latents=None,
-                conditional_latents_change_every_input=True, use_zero_map_as_unconditional=False):
+                conditional_latents_change_every_input=True, use_zero_map_as_unconditional=False, bbox_max_length=None):
         """Host -> device staging + all step-invariant work.  latents: (S, 4, h, w) initial noise shared by the views
         (:326) or (S, n_cam, 4, h, w).  conditional_latents: list[S] of list[n_cam] of clean (4, h, w) latents or None
         (StableDiffusionBEVControlNetGivenViewPipeline, pipeline_bev_controlnet_given_view.py:36-37)."""
@@ -285,7 +285,8 @@ class BEVControlNetDenoiser:
             # unconditional half of the BEV map: the scene's map, zeros on request (:296-300), or the ControlNet's
             # configured uncond map (add_uncond_to_kwargs -> substitute_with_uncond_map)
             uncond_image = torch.zeros_like(image) if use_zero_map_as_unconditional else image
-            kw = cn.add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=boxes, image=uncond_image)
+            kw = cn.add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=boxes, image=uncond_image,
+                                         max_len=bbox_max_length)
             camera_param, boxes = kw["camera_param"], kw["bboxes_3d_data"]
             text = torch.cat([negative_prompt_embeds, prompt_embeds])
             image = torch.cat([kw["image"], image])
@@ -400,7 +401,8 @@ class BEVControlNetDenoiser:
     def __call__(self, image, camera_param, prompt_embeds, negative_prompt_embeds=None, latents=None,
                  num_inference_steps: int = 50, guidance_scale: float = 2.0, bev_controlnet_kwargs: Optional[Dict] = None,
                  controlnet_conditioning_scale: float = 1.0, output_type: str = "latent", conditional_latents=None,
-                 conditional_latents_change_every_input: bool = True, use_zero_map_as_unconditional: bool = False):
+                 conditional_latents_change_every_input: bool = True, use_zero_map_as_unconditional: bool = False,
+                 bbox_max_length: Optional[int] = None):
         """Same argument meaning as the reference pipeline call (:114-160); with `conditional_latents` it is the
         given-view pipeline's call (pipeline_bev_controlnet_given_view.py:36-37).  Returns latents (S, n_cam, 4, h, w) fp32."""
         if output_type not in ("latent", "pt", "np"):
@@ -410,7 +412,7 @@ class BEVControlNetDenoiser:
         boxes = (bev_controlnet_kwargs or {}).get("bboxes_3d_data")
         st = self.prepare(latents, prompt_embeds, negative_prompt_embeds, camera_param, boxes, image, guidance_scale,
                           controlnet_conditioning_scale, conditional_latents, conditional_latents_change_every_input,
-                          use_zero_map_as_unconditional)
+                          use_zero_map_as_unconditional, bbox_max_length)
         self.set_schedule(st, num_inference_steps)
         self.run_steps(st, 0, num_inference_steps)
         latents = self.latents_out(st)

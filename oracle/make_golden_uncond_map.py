@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — tests/golden/tiny_uncond_map.pt: the reference pipeline (2 DDIM steps, CFG 2.0, tiny models)
 with (a) use_zero_map_as_unconditional=True and (b) a ControlNet built with use_uncond_map="negative1" (its `uncond_map`
-buffer replaces the unconditional half's BEV map).  Run in the build container:  python -m oracle.make_golden_uncond_map"""
+buffer replaces the unconditional half's BEV map), (c) bbox_max_length=9 (5 boxes padded to 9 masked slots).  Run in the build container:  python -m oracle.make_golden_uncond_map"""
 import os
 import sys
 
@@ -38,7 +38,8 @@ def main():
                           up_block_types=["UpDecoderBlock2D"] * 4, latent_channels=4)
     out = {}
     for name, cn_kw, call_kw in (("zero_map", {}, dict(use_zero_map_as_unconditional=True)),
-                                 ("negative1", dict(use_uncond_map="negative1", drop_cond_ratio=0.25), {})):
+                                 ("negative1", dict(use_uncond_map="negative1", drop_cond_ratio=0.25), {}),
+                                 ("max_len9", {}, dict(bbox_max_length=9))):
         mv, cn = ref_shim.build_reference_models(ucfg, ccfg, **cn_kw)
         mv.load_state_dict(usd, strict=True)
         missing = cn.load_state_dict(csd, strict=False)

@@ -450,19 +450,29 @@ class UniPC:
         return out
 
 
-def add_uncond_to_kwargs(sd: SD, ccfg, camera_param, bboxes_3d_data):
-    """BEVControlNetModel.add_uncond_to_kwargs (unet_addon_rawbox.py:625-682), max_len=None: uncond first."""
+def add_uncond_to_kwargs(sd: SD, ccfg, camera_param, bboxes_3d_data, max_len=None):
+    """BEVControlNetModel.add_uncond_to_kwargs (unet_addon_rawbox.py:625-682): uncond first; with max_len the box axis
+    of both halves is padded with empty (masked) slots, which become null tokens of the context (:637-672)."""
     b, n_cam = camera_param.shape[:2]
     cam = torch.cat([uncond_cam_param(sd, ccfg, b, n_cam).to(camera_param), camera_param])
     boxes = None
     if bboxes_3d_data is not None:
         boxes = {k: torch.cat([torch.zeros_like(v), v]) for k, v in bboxes_3d_data.items()}
+        if max_len is not None:
+            n = max_len - boxes["masks"].shape[2]
+            assert n >= 0
+            boxes = {k: torch.cat([v, torch.zeros_like(v[:, :, :1]).expand(-1, -1, n, *v.shape[3:])], dim=2)
+                     for k, v in boxes.items()}
+    elif max_len is not None:
+        boxes = dict(bboxes=torch.zeros(2 * b, n_cam, max_len, 8, 3), classes=torch.zeros(2 * b, n_cam, max_len, dtype=torch.long),
+                     masks=torch.zeros(2 * b, n_cam, max_len, dtype=torch.bool))
     return cam, boxes
 
 
 def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_prompt_embeds, camera_param,
                  bboxes_3d_data, bev_map, num_inference_steps, guidance_scale, return_all=False, scheduler="ddim",
-                 conditional_latents=None, change_every_input=True, use_zero_map_as_unconditional=False):
+                 conditional_latents=None, change_every_input=True, use_zero_map_as_unconditional=False,
+                 bbox_max_length=None):
     """StableDiffusionBEVControlNetPipeline.__call__ steps 5-8 (magicdrive/pipeline/pipeline_bev_controlnet.py:
     303-451) with DDIM eta=0 and output_type='latent'.  latents: (b, 4, h, w) initial noise (shared by the views,
     :326).  Returns (b, n_cam, 4, h, w).
@@ -482,7 +492,7 @@ def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_
     if "uncond_map" in csd:
         un_map = csd["uncond_map"][None].expand_as(bev_map).to(bev_map)
     image = torch.cat([un_map, bev_map]) if cfg_on else bev_map
-    cam, boxes = (add_uncond_to_kwargs(csd, ccfg, camera_param, bboxes_3d_data) if cfg_on
+    cam, boxes = (add_uncond_to_kwargs(csd, ccfg, camera_param, bboxes_3d_data, bbox_max_length) if cfg_on
                   else (camera_param, bboxes_3d_data))
     hist = []
     pinned = [(i, j) for i, row in enumerate(conditional_latents or []) for j, c in enumerate(row) if c is not None]

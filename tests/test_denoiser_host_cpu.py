@@ -118,7 +118,7 @@ def test_denoiser_host_logic_reproduces_reference_given_view_pipeline(cpu_standi
 
 
 @torch.no_grad()
-@pytest.mark.parametrize("case", ["zero_map", "negative1"])
+@pytest.mark.parametrize("case", ["zero_map", "negative1", "max_len9"])
 def test_unconditional_map_options_reproduce_the_reference(cpu_standins, case):
     """use_zero_map_as_unconditional (pipeline_bev_controlnet.py:296-300) and a ControlNet configured with
     use_uncond_map='negative1' (unet_addon_rawbox.py:188-202, 676-679), fixtures from the reference pipeline."""
@@ -136,10 +136,11 @@ def test_unconditional_map_options_reproduce_the_reference(cpu_standins, case):
         csd = dict(csd, uncond_map=cn.uncond_map.clone())
     cn.load_state_dict(csd)
     pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False)
-    out = _call(pipe, inp, p["steps"], p["guidance"], use_zero_map_as_unconditional=(case == "zero_map"))
+    opts = dict(use_zero_map_as_unconditional=(case == "zero_map"), bbox_max_length=9 if case == "max_len9" else None)
+    out = _call(pipe, inp, p["steps"], p["guidance"], **opts)
     ref = p["outputs"][case]
     torch.testing.assert_close(out, ref, rtol=1e-3, atol=3e-4 * ref.abs().max().item())
     orc = O.denoise_loop(usd, csd, ucfg, ccfg, inp["latents"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
                          inp["camera_param"], inp["bboxes_3d_data"], inp["bev_map"], p["steps"], p["guidance"],
-                         use_zero_map_as_unconditional=(case == "zero_map"))
+                         **opts)
     torch.testing.assert_close(orc, ref, rtol=1e-3, atol=3e-4 * ref.abs().max().item())
