@@ -17,7 +17,8 @@ ROUND_ACTIVATIONS = False
 
 
 def _act(x):
-    return x.to(torch.bfloat16).float() if ROUND_ACTIVATIONS else x.float()
+    """Output of a device operator: a fresh contiguous buffer (optionally with the device's bf16 rounding)."""
+    return (x.to(torch.bfloat16).float() if ROUND_ACTIVATIONS else x.float()).contiguous()
 
 
 def gemm_conv(a0, w, *, n_img, h_in, w_in, c0, lda0, n_out, taps=1, stride=1, pad=0, h_out=None, w_out=None, a1=None,
@@ -56,7 +57,7 @@ def gemm_conv(a0, w, *, n_img, h_in, w_in, c0, lda0, n_out, taps=1, stride=1, pa
         r2 = residual.reshape(-1, residual.shape[-1])  # the device reads it as [pixels, ldr] through a raw pointer
         assert r2.shape[0] == res.shape[0] and r2.stride(0) == ldr, (residual.shape, ldr)
         res = res + r2[:, :res.shape[1]].float()
-    res = res if out_f32 else _act(res)
+    res = res.contiguous() if out_f32 else _act(res)
     if out is not None:
         out[:, :res.shape[1]] = res
         return out
@@ -136,7 +137,7 @@ def upsample_nearest(x, n, h, w, c, ho, wo):
     xi = x.float().reshape(n, h, w, c)
     iy = torch.div(torch.arange(ho) * h, ho, rounding_mode="floor")
     ix = torch.div(torch.arange(wo) * w, wo, rounding_mode="floor")
-    return xi[:, iy][:, :, ix].reshape(n * ho * wo, c)
+    return xi[:, iy][:, :, ix].reshape(n * ho * wo, c).contiguous()
 
 
 def linear_small(x, w, bias=None, pre_silu=False, post_silu=False):

@@ -83,6 +83,17 @@ def test_denoiser_through_emulated_operators_matches_the_oracle_loop(emulated, s
 
 
 @torch.no_grad()
+def test_sd15_vae_layout_through_emulated_operators(emulated):
+    """The real SD-1.5 decoder layout (512/512/256/128 with the two channel-changing shortcuts), one small image."""
+    cfg = arch.VaeConfig()
+    sd = _bf16_exact(arch.synthetic_state_dict(arch.vae_decoder_param_shapes(cfg), 9))
+    vae = models.AutoencoderKL(**asdict(cfg))
+    vae.load_state_dict(sd)
+    z = torch.randn(1, 4, 6, 7, generator=torch.Generator().manual_seed(2))
+    assert rel_l2(vae.decode(z).sample, O.vae_decode(sd, cfg, z)) < 1e-5
+
+
+@torch.no_grad()
 @pytest.mark.parametrize("h,w", [(10, 13), (7, 9)])
 def test_vae_decoder_through_emulated_operators_matches_the_oracle(emulated, h, w):
     """VaeDecoderEngine host logic (post_quant folding, single-head attention as GEMM + row softmax + GEMM with padded
