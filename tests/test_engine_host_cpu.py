@@ -159,3 +159,25 @@ def test_cfg_streams_mode_computes_the_same_step(emulated, scheduler):
     split = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, scheduler=scheduler,
                                   cfg_streams=True)(**kw)
     assert rel_l2(split, base) < 1e-5
+
+
+@torch.no_grad()
+def test_full_sd15_width_engines_through_emulated_operators(emulated):
+    """The real SD-1.5 / MagicDrive layout (320-640-1280-1280, 8 heads, GEGLU inner 1280..5120, 13 ControlNet residuals) at a
+    small latent size: packing and sequencing of the full-width networks against the oracle (~1.3 G parameters, ~80 s)."""
+    ucfg, ccfg = arch.UNetConfig(), arch.ControlNetConfig(map_size=(8, 52, 52))
+    un, cn, usd, csd = _modules(ucfg, ccfg, 31)
+    h, w = 10, 13
+    inp = synthetic_inputs(1, 6, h, w, n_box=4, map_hw=52, seed=8)
+    lat5 = torch.stack([inp["latents"]] * 6, 1)
+    t = torch.tensor([481])
+    down, mid, ctx = cn(lat5, t, inp["camera_param"], inp["bboxes_3d_data"], inp["prompt_embeds"], inp["bev_map"],
+                        return_dict=False)
+    eps = un(lat5.reshape(-1, 4, h, w), t[0], encoder_hidden_states=ctx, down_block_additional_residuals=down,
+             mid_block_additional_residual=mid).sample
+    d32, m32, c32 = O.controlnet_forward(csd, ccfg, lat5, t, inp["camera_param"], inp["bboxes_3d_data"],
+                                         inp["prompt_embeds"], inp["bev_map"])
+    e32 = O.unet_forward(usd, ucfg, lat5.reshape(-1, 4, h, w), t[0], c32, d32, m32)
+    assert rel_l2(ctx, c32) < 1e-5 and len(down) == 12
+    assert max(rel_l2(a, b) for a, b in zip(down, d32)) < 2e-5 and rel_l2(mid, m32) < 2e-5
+    assert rel_l2(eps, e32) < 6e-3  # 16 folded connector weights rounded to bf16
