@@ -5,7 +5,9 @@ __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may 
 Parity status: PINNED.  (a) the diffusers known-answer slices the reference's own tests hold for ResnetBlock2D /
 Transformer2DModel / timestep embedding / Upsample2D / Downsample2D / DDIM (tests/test_oracle_cpu.py, numbers cited
 from third_party/diffusers/tests/...) and (b) fixtures produced by running the reference itself in the build
-container through oracle/ref_shim.py (oracle/make_golden.py -> tests/golden/*.pt).
+container through oracle/ref_shim.py (oracle/make_golden*.py -> tests/golden/*.pt: ControlNet + UNet forward, the DDIM and
+UniPC pipelines, the given-view pipeline, the unconditional-map / bbox_max_length call options, the UniPC scheduler
+trajectory, AutoencoderKL.decode).
 
 Every function takes the reference's state-dict tensors by their checkpoint names and cites the reference code
 it restates (paths relative to /root/reference).  Activations are NCHW like the reference.
