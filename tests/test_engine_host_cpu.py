@@ -181,3 +181,27 @@ def test_full_sd15_width_engines_through_emulated_operators(emulated):
     assert rel_l2(ctx, c32) < 1e-5 and len(down) == 12
     assert max(rel_l2(a, b) for a, b in zip(down, d32)) < 2e-5 and rel_l2(mid, m32) < 2e-5
     assert rel_l2(eps, e32) < 6e-3  # 16 folded connector weights rounded to bf16
+
+
+@torch.no_grad()
+def test_bf16_storage_alone_accounts_for_the_gpu_parity_gap(emulated, monkeypatch):
+    """With the operator restatements rounding every activation to bf16 exactly where the device stores one (fp32
+    arithmetic otherwise), the 3-step CFG pipeline lands 8.4e-3 (rel-L2) from the reference fixture — the same distance the
+    CUDA path measures on a B200 (profiles/parity_r1.txt: 8.2e-3 .. 8.4e-3).  The GPU tolerance (2e-2) is therefore a
+    statement about bf16 storage, not slack for kernel error."""
+    from tests.common import golden, tiny_state_dicts
+    monkeypatch.setattr(ops_emulator, "ROUND_ACTIVATIONS", True)
+    p = golden("tiny_pipeline.pt")
+    inp = p["inputs"]
+    ucfg, ccfg = tiny_configs()
+    usd, csd = tiny_state_dicts(p["seed"])
+    un = models.UNet2DConditionModelMultiview(**asdict(ucfg))
+    cn = models.BEVControlNetModel(**asdict(ccfg))
+    un.load_state_dict(usd)
+    cn.load_state_dict(csd)
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False)
+    out = pipe(image=inp["bev_map"], camera_param=inp["camera_param"], prompt_embeds=inp["prompt_embeds"],
+               negative_prompt_embeds=inp["negative_prompt_embeds"], latents=inp["latents"], num_inference_steps=p["steps"],
+               guidance_scale=p["guidance"], bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
+    e = rel_l2(out, p["latents_out"])
+    assert 4e-3 < e < 1.3e-2, e
