@@ -67,14 +67,30 @@ typedef struct {
   size_t workspace_bytes;
   int force_block_n;    /* 0 = auto; test hook */
   int force_splits;     /* 0 = auto; test hook */
-  int kernel_variant;   /* 0 = persistent double-buffered kernel (default); 1 = one-tile-per-CTA kernel; test hook */
+  int kernel_variant;   /* 0 = auto (CTA-pair kernel where it applies, else the single-CTA split-K kernel); 1 = first
+                         * one-tile-per-CTA kernel; 2 = single-CTA persistent kernel; 3 = CTA-pair kernel; 4 = the pair
+                         * kernel's code on single CTAs; test / A-B hook */
   int debug_flags;      /* ablation hook (0 in production): 1 skip stores, 2 skip epilogue loads, 4 skip TMEM loads */
   void* trace;          /* debug: device int64[8*16] receiving per-CTA clock64 stamps of the persistent kernel, or NULL */
+  /* LayerNorm folded into the GEMM (attention.py:85,104,120; blocks.py:67-71): A is the RAW tensor x, W was
+   * pre-multiplied by gamma (W' = W * gamma), bias holds c_n = sum_k beta_k W[n,k] + b_n, and the epilogue applies
+   *   out = rstd_row * (acc - mean_row * ln_colsum[n]) + c_n
+   * with mean/rstd from the per-row partial sums the PRODUCER of x wrote (stats_out of that call). */
+  const float* ln_stats;   /* fp32 [pixels, ln_parts, 2] partial (sum, sum of squares) of the rows of A, or NULL */
+  int ln_parts;
+  float ln_eps;
+  const float* ln_colsum;  /* fp32 [n_out]: sum_k W'[n, k] */
+  /* Producer side: fp32 [pixels, mdb_gemm_conv_stats_parts(d), 2] receiving partial (sum, sum of squares) of every bf16
+   * output row (after bias / residual), or NULL. */
+  float* stats_out;
 } mdb_gemm_desc;
 
 int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream);
 /* Number of kernels mdb_gemm_conv would launch for this descriptor (1, or 2 with split-K). */
 int mdb_gemm_conv_launches(const mdb_gemm_desc* d);
+/* Partial-sum slots per output row that mdb_gemm_conv writes to stats_out for this descriptor (depends on the tiling the
+ * planner picks); negative status if the descriptor cannot emit row statistics. */
+int mdb_gemm_conv_stats_parts(const mdb_gemm_desc* d);
 
 /* Direct (CUDA-core) convolution for tiny channel counts: conv_in 4->320 (unet_2d_condition.py:231),
  * conv_out 320->4 (:503), BEV map encoder (magicdrive/networks/map_embedder.py:66-76).

@@ -29,6 +29,8 @@ class GemmDesc(C.Structure):
         ("epi_mode", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("force_block_n", C.c_int), ("force_splits", C.c_int), ("kernel_variant", C.c_int), ("debug_flags", C.c_int), ("trace", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("ln_parts", C.c_int), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -40,6 +42,7 @@ SIGNATURES = {
     "mdb_device_ok": (_i, []),
     "mdb_gemm_conv": (_i, [C.POINTER(GemmDesc), _vp]),
     "mdb_gemm_conv_launches": (_i, [C.POINTER(GemmDesc)]),
+    "mdb_gemm_conv_stats_parts": (_i, [C.POINTER(GemmDesc)]),
     "mdb_conv_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "mdb_groupnorm": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     "mdb_layernorm": (_i, [_vp, _ll, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),

@@ -379,8 +379,8 @@ def synthetic_state_dict(shapes, seed: int = 0, scale: float = 1.0):
     import numpy as np
     import torch
 
-    sd = OrderedDict()
-    for name, shape in shapes.items():
+    def make(item):
+        name, shape = item
         rng = np.random.Generator(np.random.Philox(key=(seed << 32) + zlib.crc32(name.encode())))
         if name.endswith(".weight") and len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
@@ -395,5 +395,13 @@ def synthetic_state_dict(shapes, seed: int = 0, scale: float = 1.0):
             a = rng.standard_normal(shape, dtype=np.float32)
         else:  # biases, null features
             a = 0.05 * rng.standard_normal(shape, dtype=np.float32)
-        sd[name] = torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
+        return name, torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
+
+    # one independent Philox stream per tensor name: order- and thread-count-independent, so the tensors are generated
+    # in parallel (numpy releases the GIL while filling)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    items = list(shapes.items())
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        sd = OrderedDict(ex.map(make, items))
     return sd

@@ -56,11 +56,12 @@ def gather_scenes(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([bufs[r][: e - b] for r, (b, e) in enumerate(counts)], dim=0)
 
 
-def shutdown(denoisers=(), timeout_s: float = 20.0) -> None:
+def shutdown(denoisers=(), timeout_s: float = 20.0, exit_code: int = 0, hard_exit_on_timeout: bool = True) -> None:
     """Tear the process group down at the end of a run.  A CUDA graph that captured NCCL collectives (view-sharded mode)
     keeps the communicator busy: release the graphs first; if the communicator still does not come down within
-    `timeout_s` (observed on 2 x B200, NCCL 2.28.9: destroy_process_group never returned with a live graph), flush
-    and leave the process without running the remaining teardown."""
+    `timeout_s` (observed on 2 x B200, NCCL 2.28.9: destroy_process_group never returned with a live graph), warn, flush
+    and leave the process with `exit_code` (the status the caller would have returned) without running the remaining
+    teardown; with hard_exit_on_timeout=False the caller gets control back instead."""
     for d in denoisers:
         d.release_graph()
     gc.collect()
@@ -72,9 +73,12 @@ def shutdown(denoisers=(), timeout_s: float = 20.0) -> None:
     t.start()
     t.join(timeout_s)
     if t.is_alive():
+        sys.stderr.write(f"[magicdrive_b200.dist] destroy_process_group still running after {timeout_s:.0f} s; "
+                         + ("leaving the process without it\n" if hard_exit_on_timeout else "returning without it\n"))
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        if hard_exit_on_timeout:
+            os._exit(exit_code)
 
 
 def max_over_ranks(value: float, device) -> float:

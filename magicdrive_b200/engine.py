@@ -44,6 +44,9 @@ def _f32(t):
 class _Weights:
     """Packs a reference state dict into kernel-ready device tensors (bf16 K-major matrices, fp32 biases)."""
 
+    fold_dtype = BF16  # storage of weights that are PRODUCTS of checkpoint tensors (W * gamma); the CPU host-logic tests
+    #                    set fp32 so that the fold's algebra is checked to 1e-5, apart from its bf16 rounding
+
     def __init__(self, sd: Dict[str, torch.Tensor], device):
         self.sd = sd
         self.device = device
@@ -108,6 +111,25 @@ class _Weights:
             w, b = pack_geglu(self.raw(p + ".weight").float(), self.raw(p + ".bias").float())
             self.t[p + ".gw"], self.t[p + ".gb"] = w, b
         return self.t[p + ".gw"], self.t[p + ".gb"]
+
+    def ln_lin(self, name, norm, prefixes, geglu=False):
+        """LayerNorm `norm` folded into the linear(s) `prefixes` that consume it (mdb_gemm_desc.ln_*):
+        W' = W * gamma (bf16), c = W beta + b (fp32), colsum_n = sum_k W'[n, k] (of the rounded W', fp32).
+        Returns (W', c, colsum); with geglu the three are re-ordered to the kernel's [128 value | 128 gate] tiles."""
+        if name + ".w" not in self.t:
+            w = torch.cat([self.raw(p + ".weight").float() for p in prefixes], 0)
+            b = torch.cat([self.raw(p + ".bias").float() if (p + ".bias") in self.sd
+                           else torch.zeros(self.sd[p + ".weight"].shape[0], device=w.device) for p in prefixes], 0)
+            g, beta = self.raw(norm + ".weight").float(), self.raw(norm + ".bias").float()
+            wg = (w * g[None, :]).to(self.fold_dtype)
+            c = w @ beta + b
+            cs = wg.float().sum(1)
+            if geglu:
+                wg2, c = pack_geglu(wg.float(), c, dtype=self.fold_dtype)
+                _, cs = pack_geglu(wg.float(), cs)
+                wg = wg2
+            self.t[name + ".w"], self.t[name + ".c"], self.t[name + ".cs"] = wg.contiguous(), _f32(c), _f32(cs)
+        return self.t[name + ".w"], self.t[name + ".c"], self.t[name + ".cs"]
 
     def folded_connector(self, blk):
         """W' = Wc @ Wo, b' = 2 Wc b_o + b_c  (fp32 fold, bf16 storage)."""
@@ -231,52 +253,48 @@ class _Net:
         g, b = W.norm(p + ".norm")
         h = ops.groupnorm(x.data, C, C, V, L, g, b, 1e-6, False, groups=cfg.norm_num_groups)
         wi, bi = W.conv(p + ".proj_in")
-        X = ops.linear(h, wi, bias=bi)
+        # The block's LayerNorms never run as kernels: every GEMM that writes the residual stream X also emits per-row
+        # (sum, sum of squares) of the bf16 values it stores, and the GEMM that consumes LayerNorm(X) reads the raw X
+        # with gamma folded into its weights and normalises in its epilogue (mdb_gemm_desc.ln_stats / stats_out).
+        X, sx = ops.linear(h, wi, bias=bi, emit_stats=True)
         # --- self attention
-        g, b = W.norm(blk + ".norm1")
-        n1 = ops.layernorm(X, g, b)
-        wqkv = W.cat_lin(blk + ".attn1.wqkv", [blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
-        qkv = ops.linear(n1, wqkv)
+        wqkv, cq, sq = W.ln_lin(blk + ".attn1.lnqkv", blk + ".norm1", [blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
+        qkv = ops.linear(X, wqkv, bias=cq, ln=sx, ln_colsum=sq)
         o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C, ldk=3 * C,
                           ldv=3 * C, scale=scale)
         wo, bo = W.lin(blk + ".attn1.to_out.0")
-        X = ops.linear(o, wo, bias=bo, residual=X)
+        X, sx = ops.linear(o, wo, bias=bo, residual=X, emit_stats=True)
         # --- conditioning cross attention (camera + text + box tokens)
-        g, b = W.norm(blk + ".norm2")
-        n2 = ops.layernorm(X, g, b)
-        wq, _ = W.lin(blk + ".attn2.to_q", bias=False)
-        q = ops.linear(n2, wq)
+        wq, cq, sq = W.ln_lin(blk + ".attn2.lnq", blk + ".norm2", [blk + ".attn2.to_q"])
+        q = ops.linear(X, wq, bias=cq, ln=sx, ln_colsum=sq)
         kv = ctx_kv[p]
         o = ops.attention(q, kv, kv[:, C:], b=V, heads=heads, lq=L, lk=lc, d=d, ldq=C, ldk=2 * C, ldv=2 * C, scale=scale)
         wo, bo = W.lin(blk + ".attn2.to_out.0")
-        X = ops.linear(o, wo, bias=bo, residual=X)
+        X, sx = ops.linear(o, wo, bias=bo, residual=X, emit_stats=True)
         # --- cross-view attention
         if tr.multiview:
             if cfg.neighboring_attn_type != "add" or cfg.zero_module_type != "zero_linear":
                 raise NotImplementedError("only neighboring_attn_type='add' with the zero_linear connector (the shipped "
                                           "configs/model/SDv1.5mv_rawbox.yaml:19-20) is implemented")
-            g, b = W.norm(blk + ".norm4")
-            n4 = ops.layernorm(X, g, b)
             if self.view_shard is None:
-                wqkv = W.cat_lin(blk + ".attn4.wqkv", [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
-                qkv = ops.linear(n4, wqkv)
+                wqkv, cq, sq = W.ln_lin(blk + ".attn4.lnqkv", blk + ".norm4",
+                                        [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
+                qkv = ops.linear(X, wqkv, bias=cq, ln=sx, ln_colsum=sq)
                 o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C,
                                   ldk=3 * C, ldv=3 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
             else:
                 # cameras split across ranks: local queries, K/V of every rank's views all-gathered over NVLink
-                wq, _ = W.lin(blk + ".attn4.to_q", bias=False)
-                wkv = W.cat_lin(blk + ".attn4.wkv", [blk + ".attn4.to_k", blk + ".attn4.to_v"])
-                q = ops.linear(n4, wq)
-                kv = self.view_shard.all_gather_rows(ops.linear(n4, wkv))
+                wq, cq, sq = W.ln_lin(blk + ".attn4.lnq", blk + ".norm4", [blk + ".attn4.to_q"])
+                wkv, ckv, skv = W.ln_lin(blk + ".attn4.lnkv", blk + ".norm4", [blk + ".attn4.to_k", blk + ".attn4.to_v"])
+                q = ops.linear(X, wq, bias=cq, ln=sx, ln_colsum=sq)
+                kv = self.view_shard.all_gather_rows(ops.linear(X, wkv, bias=ckv, ln=sx, ln_colsum=skv))
                 o = ops.attention(q, kv, kv[:, C:], b=V, b_kv=V * self.view_shard.world, heads=heads, lq=L, lk=L, d=d,
                                   ldq=C, ldk=2 * C, ldv=2 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
             wf, bf_ = W.folded_connector(blk)
-            X = ops.linear(o, wf, bias=bf_, residual=X)
+            X, sx = ops.linear(o, wf, bias=bf_, residual=X, emit_stats=True)
         # --- GEGLU feed-forward
-        g, b = W.norm(blk + ".norm3")
-        n3 = ops.layernorm(X, g, b)
-        wg, bg = W.geglu(blk + ".ff.net.0.proj")
-        hg = ops.linear(n3, wg, bias=bg, geglu=True)
+        wg, cg, sg = W.ln_lin(blk + ".ff.lnproj", blk + ".norm3", [blk + ".ff.net.0.proj"], geglu=True)
+        hg = ops.linear(X, wg, bias=cg, geglu=True, ln=sx, ln_colsum=sg)
         w2, b2 = W.lin(blk + ".ff.net.2")
         X = ops.linear(hg, w2, bias=b2, residual=X)
         wp, bp = W.conv(p + ".proj_out")

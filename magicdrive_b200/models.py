@@ -72,6 +72,7 @@ class _B200Module(nn.Module):
         self._engine = None
         self._engine_key = None
         self._ctx_cache = {}
+        self._view_shard = None  # re-applied to every engine this module builds (engines are rebuilt when weights change)
 
     # -- nn.Module conveniences the pipeline relies on (pipeline_utils.py:624, 664-685)
     @property
@@ -131,7 +132,15 @@ class _B200Module(nn.Module):
             raise ops._lib.MdbError(f"{type(self).__name__} runs only on a CUDA (sm_100a) device; parameters are on {dev}")
         if self._engine is None:
             self._engine = cls_(self.arch_cfg, dict(self.state_dict()), dev)
+            if self._view_shard is not None and hasattr(self._engine, "set_view_shard"):
+                self._engine.set_view_shard(self._view_shard)
         return self._engine
+
+    def set_view_shard(self, shard) -> None:
+        """Split the cameras across ranks (dist.ViewShard) or None; survives engine rebuilds (load_state_dict / .to())."""
+        self._view_shard = shard
+        if self._engine is not None and hasattr(self._engine, "set_view_shard"):
+            self._engine.set_view_shard(shard)
 
 
 def _timesteps_f32(timestep, n, device):

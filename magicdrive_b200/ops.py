@@ -16,7 +16,7 @@ from ._lib import GemmDesc, check
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-GEMM_VARIANT = int(__import__('os').environ.get('MDB_GEMM_VARIANT', '0'))  # test/bench hook: 1 = non-persistent kernel
+GEMM_VARIANT = int(os.environ.get('MDB_GEMM_VARIANT', '0'))  # A/B hook: mdb_gemm_desc.kernel_variant (2 = single-CTA kernel, 3 = CTA pairs)
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 _profile = None  # when a list: (kind, algorithmic flops, start event, end event) per tensor-core launch
 
@@ -106,6 +106,14 @@ def workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+class RowStats:
+    """Per-row partial (sum, sum of squares) of a bf16 [rows, C] tensor, fp32 [rows, parts, 2], written by the epilogue of
+    the GEMM that produced the tensor and consumed by a GEMM with a folded LayerNorm."""
+
+    def __init__(self, data: torch.Tensor, parts: int):
+        self.data, self.parts = data, parts
+
+
 def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in: int, c0: int, lda0: int,
               n_out: int, taps: int = 1, stride: int = 1, pad: int = 0, h_out: Optional[int] = None,
               w_out: Optional[int] = None, a1: Optional[torch.Tensor] = None, c1: int = 0, lda1: int = 0,
@@ -113,9 +121,14 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
               residual: Optional[torch.Tensor] = None, ldr: int = 0, out: Optional[torch.Tensor] = None,
               ldo: Optional[int] = None, out_f32: bool = False, out_scale: float = 1.0, geglu: bool = False,
               force_block_n: int = 0, force_splits: int = 0, allow_split_k: bool = True,
-              kernel_variant: int = 0, trace: Optional[torch.Tensor] = None, debug_flags: int = 0) -> torch.Tensor:
+              kernel_variant: int = 0, trace: Optional[torch.Tensor] = None, debug_flags: int = 0,
+              ln: Optional["RowStats"] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+              emit_stats: bool = False):
     """tcgen05 GEMM / implicit-GEMM conv (mdb_gemm_conv).  `a0` (and `a1`) are NHWC bf16 buffers whose pixel
-    stride is lda* elements; `w` is bf16 [n_out, taps*taps*(c0+c1)]."""
+    stride is lda* elements; `w` is bf16 [n_out, taps*taps*(c0+c1)].
+    ln / ln_colsum: fold a LayerNorm of the rows of `a0` into this GEMM (`ln` = the RowStats the producer of `a0`
+    emitted, `w` pre-multiplied by gamma, `bias` = beta-term + bias).  emit_stats: also return the RowStats of the
+    output rows -> (out, RowStats)."""
     global _launches
     _need_cuda(a0, w)
     if h_out is None:
@@ -153,17 +166,27 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
     d.trace = _ptr(trace)
     d.debug_flags = debug_flags
     L = _lib.lib()
+    if ln is not None:
+        d.ln_stats, d.ln_parts, d.ln_eps, d.ln_colsum = ln.data.data_ptr(), ln.parts, float(ln_eps), _ptr(ln_colsum)
+    stats = None
+    if emit_stats:
+        d.stats_out = 1  # any non-null value: the planner only asks whether statistics are wanted
+        parts = L.mdb_gemm_conv_stats_parts(C.byref(d))
+        if parts <= 0:
+            check(parts, "mdb_gemm_conv_stats_parts")
+        stats = RowStats(torch.empty((pixels, parts, 2), dtype=F32, device=a0.device), parts)
+        d.stats_out = stats.data.data_ptr()
     e0 = _prof_begin()
     check(L.mdb_gemm_conv(C.byref(d), _stream()), "mdb_gemm_conv")
     _prof_end("gemm_conv", 2.0 * pixels * n_out * taps * taps * (c0 + c1), e0,
               f"M={pixels} N={n_out} K={taps * taps * (c0 + c1)} img={n_img}x{h_out}x{w_out} taps={taps} s={stride} "
               f"geglu={int(geglu)} res={int(residual is not None)}")
     _launches += L.mdb_gemm_conv_launches(C.byref(d))
-    return out
+    return (out, stats) if emit_stats else out
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, ldo=None, geglu=False,
-           out_f32=False, out_scale=1.0, **kw) -> torch.Tensor:
+           out_f32=False, out_scale=1.0, **kw):
     """Token GEMM: x [M, K] bf16 (row stride may exceed K), w [N, K] bf16."""
     m, k = x.shape
     return gemm_conv(x, w, n_img=1, h_in=1, w_in=m, c0=k, lda0=x.stride(0), n_out=w.shape[0], bias=bias,
@@ -183,25 +206,6 @@ def conv_direct(x, wgt, bias, *, n, h, w, cin, cout, k, stride=(1, 1), pad=(1, 1
                                      _ptr(out), int(out_f32), _stream()), "mdb_conv_direct")
     _launches += 1
     return out
-
-
-_gn_ws = {}
-_ws_slot = 0
-
-
-class workspace_slot:
-    """Select which split-K scratch buffer the enclosed launches use (slot 1 = the concurrent ControlNet stream)."""
-
-    def __init__(self, slot):
-        self.slot = slot
-
-    def __enter__(self):
-        global _ws_slot
-        self.prev, _ws_slot = _ws_slot, self.slot
-
-    def __exit__(self, *a):
-        global _ws_slot
-        _ws_slot = self.prev
 
 
 def groupnorm(x0, c0, ld0, n_img, hw, gamma, beta, eps, silu, x1=None, c1=0, ld1=0, groups=32):

@@ -8,7 +8,7 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(torch.bfloat16)
 
 
-def pack_geglu(w: torch.Tensor, b: torch.Tensor, tile: int = 256):
+def pack_geglu(w: torch.Tensor, b: torch.Tensor, tile: int = 256, dtype=torch.bfloat16):
     """GEGLU.proj (attention.py:270) [2*inner, C]: rows [0, inner) are the value half, [inner, 2*inner) the gate
     half.  Re-order rows so every `tile`-row block holds tile/2 value rows followed by the matching gate rows;
     the GEMM epilogue then forms value * gelu(gate) inside one CTA tile."""
@@ -21,4 +21,4 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor, tile: int = 256):
         idx += list(range(j * half, (j + 1) * half))
         idx += list(range(inner + j * half, inner + (j + 1) * half))
     idx = torch.tensor(idx, device=w.device)
-    return w[idx].contiguous().to(torch.bfloat16), b[idx].contiguous().float()
+    return w[idx].contiguous().to(dtype), b[idx].contiguous().float()

@@ -152,13 +152,15 @@ class BEVControlNetDenoiser:
         self.overlap_controlnet = overlap_controlnet
         self.cfg_streams = cfg_streams
         self.view_shard = view_shard
-        unet.engine().set_view_shard(view_shard)
+        unet.set_view_shard(view_shard)
         self._side = {}
+        self.generator = None  # optional torch.Generator for latents=None calls
         self.scheduler_name = scheduler
         self.scheduler = DDIMSchedule() if scheduler == "ddim" else UniPCSchedule()
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._graph_key = None
+        self._graph_state = None
         self._static = None
 
     def release_graph(self):
@@ -260,12 +262,22 @@ class BEVControlNetDenoiser:
     @torch.no_grad()
     def prepare(self, latents, prompt_embeds, negative_prompt_embeds, camera_param, bboxes_3d_data, image,
                 guidance_scale=2.0, controlnet_conditioning_scale=1.0, conditional_latents=None,
-                conditional_latents_change_every_input=True, use_zero_map_as_unconditional=False, bbox_max_length=None):
+                conditional_latents_change_every_input=True, use_zero_map_as_unconditional=False, bbox_max_length=None,
+                latent_hw=None):
         """Host -> device staging + all step-invariant work.  latents: (S, 4, h, w) initial noise shared by the views
         (:326) or (S, n_cam, 4, h, w).  conditional_latents: list[S] of list[n_cam] of clean (4, h, w) latents or None
         (StableDiffusionBEVControlNetGivenViewPipeline, pipeline_bev_controlnet_given_view.py:36-37)."""
         dev = self.unet.device
         cn, un = self.controlnet, self.unet
+        if camera_param is None:
+            # the reference falls back to the learned null camera and switches guidance off (pipeline_bev_controlnet.py:
+            # 330-338): there is no conditional camera to guide towards
+            camera_param = cn.uncond_cam_param([image.shape[0], len(un.arch_cfg.neighboring_view_pair)]).float().cpu()
+            guidance_scale = 1.0
+        if latents is None:
+            # prepare_latents (pipeline_bev_controlnet.py:316-327): one noise tensor per scene, shared by its views
+            hh, ww = latent_hw if latent_hw is not None else (un.arch_cfg.sample_size, un.arch_cfg.sample_size)
+            latents = torch.randn(camera_param.shape[0], un.arch_cfg.in_channels, hh, ww, generator=self.generator)
         cfg = guidance_scale > 1.0
         if self.view_shard is not None:
             if latents.dim() == 4:
@@ -309,7 +321,9 @@ class BEVControlNetDenoiser:
             pin_cond = torch.stack([torch.zeros(c, h, w) if x is None else x.to("cpu", F32)
                                     for row in conditional_latents for x in row])
             pin_cond = pin_cond.to(dev).permute(0, 2, 3, 1).contiguous().view(-1, c)
-        sig = (V, h, w, cfg, lc, S, n_cam, pin_mode)
+        # the resident state (and the captured graph) hold pointers into the engines' packed weights: a rebuilt engine
+        # (load_state_dict, .to(), BEVControlNetModel.prepare) must invalidate both
+        sig = (V, h, w, cfg, lc, S, n_cam, pin_mode, id(un.engine()), id(cn.engine()))
         st = self._static
         if st is not None and st["sig"] == sig:
             # same shapes as the resident state: refresh its buffers in place so a captured graph stays valid
@@ -402,7 +416,8 @@ class BEVControlNetDenoiser:
                  num_inference_steps: int = 50, guidance_scale: float = 2.0, bev_controlnet_kwargs: Optional[Dict] = None,
                  controlnet_conditioning_scale: float = 1.0, output_type: str = "latent", conditional_latents=None,
                  conditional_latents_change_every_input: bool = True, use_zero_map_as_unconditional: bool = False,
-                 bbox_max_length: Optional[int] = None):
+                 bbox_max_length: Optional[int] = None, height: Optional[int] = None, width: Optional[int] = None,
+                 generator: Optional[torch.Generator] = None):
         """Same argument meaning as the reference pipeline call (:114-160); with `conditional_latents` it is the
         given-view pipeline's call (pipeline_bev_controlnet_given_view.py:36-37).  Returns latents (S, n_cam, 4, h, w) fp32."""
         if output_type not in ("latent", "pt", "np"):
@@ -410,11 +425,14 @@ class BEVControlNetDenoiser:
         if output_type != "latent" and self.vae is None:
             raise ValueError("output_type 'pt' / 'np' needs the denoiser to be built with vae=AutoencoderKL(...)")
         boxes = (bev_controlnet_kwargs or {}).get("bboxes_3d_data")
+        self.generator = generator
+        ss = self.unet.arch_cfg.sample_size * 8  # the reference's default height / width (pipeline_controlnet.py: sample_size * vae_scale_factor)
         st = self.prepare(latents, prompt_embeds, negative_prompt_embeds, camera_param, boxes, image, guidance_scale,
                           controlnet_conditioning_scale, conditional_latents, conditional_latents_change_every_input,
-                          use_zero_map_as_unconditional, bbox_max_length)
-        self.set_schedule(st, num_inference_steps)
-        self.run_steps(st, 0, num_inference_steps)
+                          use_zero_map_as_unconditional, bbox_max_length,
+                          latent_hw=((height or ss) // 8, (width or ss) // 8))
+        ts = self.set_schedule(st, num_inference_steps)
+        self.run_steps(st, 0, len(ts))  # UniPC drops duplicate rounded timesteps: run what the schedule holds
         latents = self.latents_out(st)
         if output_type == "latent":
             return latents

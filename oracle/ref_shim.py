@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — import the *reference itself* (read-only tree at /root/reference) on a 2026 stack.
 
-Only usable in the build container (the GPU box has no /root/reference).  It is used by `oracle/make_golden.py`
-to generate the committed fixtures under tests/golden/ and by CPU tests that are skipped when the tree is
-absent.  The reference's vendored diffusers 0.17.1 does not import against transformers 5.x / huggingface_hub 1.x,
+In the build container it reads /root/reference in place; on the GPU box (no /root/reference) it reads the byte-for-byte
+snapshot of the same .py files that `oracle/make_ref_snapshot.py` put under oracle/_ref (git-ignored).  It is used by
+`oracle/make_golden*.py` to generate the committed fixtures under tests/golden/, by `oracle/ref_runner.py`
+(`bench.py --impl reference` and the gpu_reference measurement) and by tests that are skipped when neither tree exists.  The reference's vendored diffusers 0.17.1 does not import against transformers 5.x / huggingface_hub 1.x,
 so the package is registered as a namespace module and a handful of removed symbols are stubbed (SURVEY.md §8c,
 Appendix C).  Nothing in the product imports this file.
 """
@@ -11,7 +12,8 @@ import os
 import sys
 import types
 
-REF = os.environ.get("MAGICDRIVE_REFERENCE", "/root/reference")
+_SNAPSHOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/make_ref_snapshot.py
+REF = os.environ.get("MAGICDRIVE_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/magicdrive") else _SNAPSHOT)
 SRC = os.path.join(REF, "third_party/diffusers/src/diffusers")
 _loaded = None
 

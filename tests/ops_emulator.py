@@ -23,7 +23,7 @@ def _act(x):
 
 def gemm_conv(a0, w, *, n_img, h_in, w_in, c0, lda0, n_out, taps=1, stride=1, pad=0, h_out=None, w_out=None, a1=None,
               c1=0, lda1=0, bias=None, rowbias=None, residual=None, ldr=0, out=None, ldo=None, out_f32=False,
-              out_scale=1.0, geglu=False, **_):
+              out_scale=1.0, geglu=False, ln=None, ln_colsum=None, ln_eps=1e-5, emit_stats=False, **_):
     if h_out is None:
         h_out = (h_in + 2 * pad - taps) // stride + 1
     if w_out is None:
@@ -41,6 +41,12 @@ def gemm_conv(a0, w, *, n_img, h_in, w_in, c0, lda0, n_out, taps=1, stride=1, pa
     acc = F.conv2d(x, w4, stride=stride, padding=pad)
     assert acc.shape[2:] == (h_out, w_out)
     acc = acc.permute(0, 2, 3, 1).reshape(n_img * h_out * w_out, n_out)
+    if ln is not None:  # folded LayerNorm: rstd * (acc - mean * colsum) with the producer's row statistics
+        assert taps == 1 and ln.data.shape[0] == acc.shape[0]
+        tot = ln.data.float().sum(1)
+        mean = tot[:, 0:1] / cin
+        var = (tot[:, 1:2] / cin - mean * mean).clamp_min(0)
+        acc = torch.rsqrt(var + ln_eps) * (acc - mean * ln_colsum.float()[None, :])
     if bias is not None:
         acc = acc + bias.float()
     if rowbias is not None:
@@ -58,17 +64,24 @@ def gemm_conv(a0, w, *, n_img, h_in, w_in, c0, lda0, n_out, taps=1, stride=1, pa
         assert r2.shape[0] == res.shape[0] and r2.stride(0) == ldr, (residual.shape, ldr)
         res = res + r2[:, :res.shape[1]].float()
     res = res.contiguous() if out_f32 else _act(res)
+    stats = None
+    if emit_stats:  # two partial slots per row, like a one-tile launch of the device kernel
+        rr = res.float()  # the device accumulates the values it stores (already bf16-rounded when ROUND_ACTIVATIONS)
+        half = res.shape[1] // 2
+        parts = torch.stack([torch.stack([rr[:, :half].sum(1), (rr[:, :half] ** 2).sum(1)], -1),
+                             torch.stack([rr[:, half:].sum(1), (rr[:, half:] ** 2).sum(1)], -1)], 1)
+        stats = ops.RowStats(parts.contiguous(), 2)
     if out is not None:
         out[:, :res.shape[1]] = res
-        return out
-    return res
+        return (out, stats) if emit_stats else out
+    return (res, stats) if emit_stats else res
 
 
 def linear(x, w, bias=None, residual=None, out=None, ldo=None, geglu=False, out_f32=False, out_scale=1.0, **kw):
     m, k = x.shape
     return gemm_conv(x, w, n_img=1, h_in=1, w_in=m, c0=k, lda0=x.stride(0), n_out=w.shape[0], bias=bias,
                      residual=residual, ldr=(residual.stride(0) if residual is not None else 0), out=out, ldo=ldo,
-                     geglu=geglu, out_f32=out_f32, out_scale=out_scale)
+                     geglu=geglu, out_f32=out_f32, out_scale=out_scale, **kw)
 
 
 def conv_direct(x, wgt, bias, *, n, h, w, cin, cout, k, stride=(1, 1), pad=(1, 1), silu=False, residual=None, out_f32=False):
