@@ -304,10 +304,10 @@ int launch3_bn(const Plan3& pl, const CUtensorMap& tA0, const CUtensorMap& tA1, 
 int choose_kernel(const mdb_gemm_desc* d, const Plan& old_plan) {
   const bool wants_fold = d->ln_stats != nullptr || d->stats_out != nullptr;
   if (!pair_supported(d, old_plan)) return 0;
+  if (wants_fold) return d->kernel_variant == 4 ? 1 : 2;  // only gemm_pair_kernel has the folded-LayerNorm epilogue
   if (d->kernel_variant == 2) return 0;
   if (d->kernel_variant == 3) return 2;
   if (d->kernel_variant == 4) return 1;
-  if (wants_fold) return 2;
   if (old_plan.splits > 1) return 0;  // few tiles and a deep K: split-K on the single-CTA kernel fills the machine
   return 2;
 }
@@ -381,6 +381,7 @@ extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
     gp.epi_mode = d->epi_mode;
     gp.bias = d->bias, gp.rowbias = d->rowbias, gp.rowbias_ld = d->rowbias_ld;
     gp.out = d->out, gp.ldo = d->ldo, gp.out_scale = d->out_scale;
+    gp.trace = static_cast<long long*>(d->trace);
     g3.m_tiles = p3.m_tiles, g3.m_groups = p3.m_groups, g3.n_tiles = p3.n_tiles;
     g3.out_cols = out_cols;
     g3.use_res_tma = d->residual ? 1 : 0;

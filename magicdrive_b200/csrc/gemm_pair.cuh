@@ -102,6 +102,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int out_per_tile = geglu ? BLOCK_N / 2 : BLOCK_N;
   const int ch_tile = geglu ? CH_GLU : CH_LIN;
 
+  // optional per-CTA phase stamps (debug / tools/bench_gemm.py --trace): 16 int64 slots per CTA, globaltimer ns
+  long long* trace = (p.trace != nullptr && blockIdx.x < 160) ? p.trace + blockIdx.x * 16 : nullptr;
+#define MDB_TRACE3(slot)                                                    \
+  do {                                                                      \
+    if (trace) {                                                            \
+      unsigned long long t__;                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));               \
+      trace[slot] = static_cast<long long>(t__);                            \
+    }                                                                       \
+  } while (0)
+  if (threadIdx.x == 0) MDB_TRACE3(0);
+
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
@@ -137,6 +149,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) MDB_TRACE3(1);
 
   if (warp == 0) {
     // =========================== TMA producer (one lane) ===========================
@@ -179,6 +192,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
+      MDB_TRACE3(2);
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA of the pair) ===========================
@@ -218,7 +232,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             phase ^= 1;
           }
         }
+        if (lane == 0 && it == 0) MDB_TRACE3(7);
       }
+      if (lane == 0) MDB_TRACE3(3);
     }
   } else if (warp == 2) {
     // =========================== staging-buffer manager: residual loads + output stores (one lane) ==============
@@ -268,7 +284,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         ++sto_k;
         if (++sto_c == chunks_of(sto_t)) sto_c = 0, sto_t += n_clusters;
       }
+      MDB_TRACE3(4);
       bulk_wait_group_all();
+      MDB_TRACE3(5);
     }
     __syncwarp();
   } else {
@@ -425,11 +443,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
         else mbar_arrive(&acc_empty[as]);
       }
+      if (warp == 3 && lane == 0 && it == 0) MDB_TRACE3(8);
     }
+    if (warp == 3 && lane == 0) MDB_TRACE3(6);
   }
 
   __syncwarp();
+  if (threadIdx.x == 0) MDB_TRACE3(9);
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) MDB_TRACE3(10);
+#undef MDB_TRACE3
   if (warp == 2) {
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);

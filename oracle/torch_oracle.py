@@ -509,10 +509,10 @@ def denoise_loop(usd: SD, csd: SD, ucfg, ccfg, latents, prompt_embeds, negative_
             for i, j in pinned:
                 lat[i, j] = sched.add_noise(conditional_latents[i][j], noise0[i, j], t)
         inp = torch.cat([lat] * 2) if cfg_on else lat
-        tt = torch.full((inp.shape[0],), t, dtype=torch.int64)
+        tt = torch.full((inp.shape[0],), t, dtype=torch.int64, device=inp.device)
         down, mid, ctx = controlnet_forward(csd, ccfg, inp, tt, cam, boxes, text, image)
         x = inp.reshape(-1, *inp.shape[2:])
-        eps = unet_forward(usd, ucfg, x, torch.tensor(t), ctx, down, mid)
+        eps = unet_forward(usd, ucfg, x, torch.tensor(t, device=inp.device), ctx, down, mid)
         if cfg_on:
             eu, ec = eps.chunk(2)
             eps = eu + guidance_scale * (ec - eu)

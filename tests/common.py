@@ -46,3 +46,18 @@ def to_dev(x, dev, dtype=None):
             return x.to(dev, dtype)
         return x.to(dev)
     return x
+
+
+def record(line: str, name: str = "parity_gpu_latest.txt"):
+    """Print a `[parity]` / `[speed]` evidence line and append it to profiles/<name> (and gpurun_out/<name> when that
+    directory exists), so that a GPU run of the test-suite leaves its measured numbers behind (pytest -q hides stdout)."""
+    print(line)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in ("profiles", "gpurun_out"):
+        dd = os.path.join(root, d)
+        if os.path.isdir(dd):
+            try:
+                with open(os.path.join(dd, name), "a") as fh:
+                    fh.write(line.rstrip("\n") + "\n")
+            except OSError:
+                pass

@@ -2,9 +2,10 @@
  (1) fixtures produced by the REFERENCE itself (tests/golden/*.pt, made by oracle/make_golden.py) and
  (2) the fp32 oracle at SD-1.5 size.
 Tolerance: bf16 storage cannot meet rtol 1e-3 / atol 1e-4 elementwise (the reference's own bf16 forward differs from
-its fp32 forward by more, SURVEY.md §7 "Tolerance"); the criterion is  err(ours-bf16 vs fp32 truth) <=
-1.5 x err(reference-arithmetic-in-bf16 vs fp32 truth) + 2e-3, where "reference arithmetic in bf16" is the oracle
-restatement run with bf16 weights/activations through torch's own CUDA kernels."""
+its fp32 forward by more, SURVEY.md section 7 "Tolerance"; the fp32 oracle does meet it literally against the reference at full
+size, tests/test_oracle_cpu.py); the criterion is  err(ours-bf16 vs fp32 truth) <= 1.0 x err(reference-arithmetic-in-bf16 vs
+fp32 truth) + 5e-4  at every tap, where "reference arithmetic in bf16" is the oracle restatement run with bf16
+weights/activations through torch's own CUDA kernels.  Every measured number is appended to profiles/parity_gpu_latest.txt."""
 import os
 from dataclasses import asdict
 
@@ -17,7 +18,7 @@ from magicdrive_b200 import arch  # noqa: E402
 from magicdrive_b200.models import BEVControlNetModel, UNet2DConditionModelMultiview  # noqa: E402
 from magicdrive_b200.pipeline import BEVControlNetDenoiser  # noqa: E402
 from oracle import torch_oracle as O  # noqa: E402  (checker only)
-from tests.common import golden, max_rel, rel_l2, tiny_configs, tiny_state_dicts, to_dev  # noqa: E402
+from tests.common import golden, max_rel, record, rel_l2, tiny_configs, tiny_state_dicts, to_dev  # noqa: E402
 
 DEV = "cuda"
 
@@ -37,10 +38,10 @@ def _bf16_yardstick(fn, usd, csd):
     return fn(ub, cb, torch.bfloat16)
 
 
-def _check(name, ours, truth, yard, slack=2e-3, factor=1.5):
+def _check(name, ours, truth, yard, slack=5e-4, factor=1.0):
     e_ours, e_ref = rel_l2(ours, truth), rel_l2(yard, truth)
-    print(f"[parity] {name}: rel-L2 ours {e_ours:.3e}  reference-bf16 {e_ref:.3e}  max-rel ours {max_rel(ours, truth):.3e}"
-          f" ref {max_rel(yard, truth):.3e}")
+    record(f"[parity] {name}: rel-L2 ours {e_ours:.3e}  reference-bf16 {e_ref:.3e}  max-rel ours {max_rel(ours, truth):.3e}"
+           f" ref {max_rel(yard, truth):.3e}")
     assert e_ours <= factor * e_ref + slack, (name, e_ours, e_ref)
 
 
@@ -95,7 +96,7 @@ def test_tiny_pipeline_vs_reference_fixture(cuda_lib, graph):
                bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
     assert out.shape == g["latents_out"].shape
     e = rel_l2(out, g["latents_out"])
-    print(f"[parity] pipeline(graph={graph}): rel-L2 {e:.3e} max-rel {max_rel(out, g['latents_out']):.3e}")
+    record(f"[parity] pipeline(graph={graph}): rel-L2 {e:.3e} max-rel {max_rel(out, g['latents_out']):.3e}")
     assert e < 2e-2
     # views must differ (cross-view attention and per-view cameras are live)
     assert (out[:, 0] - out[:, 1]).abs().max() > 1e-3
@@ -140,7 +141,50 @@ def test_sd15_forward_vs_fp32_oracle(cuda_lib, h, w, map_hw):
     # the literal north-star tolerance, reported (not asserted): fraction of elements within rtol 1e-3 / atol 1e-4
     ok = torch.isclose(eps.float(), e32, rtol=1e-3, atol=1e-4).float().mean().item()
     ok_ref = torch.isclose(ye.float(), e32, rtol=1e-3, atol=1e-4).float().mean().item()
-    print(f"[parity] literal rtol1e-3/atol1e-4 pass fraction: ours {ok:.3f}, reference-bf16 {ok_ref:.3f}")
+    record(f"[parity] sd15 {h}x{w} literal rtol1e-3/atol1e-4 pass fraction: ours {ok:.3f}, reference-bf16 {ok_ref:.3f}")
+    if (h, w) == (28, 50):
+        # the same step against the REFERENCE's own output (tests/golden/sd15_forward.pt <- oracle/make_golden_sd15.py)
+        g = golden("sd15_forward.pt")
+        assert (g["seeds"], g["input_seed"], g["t"], g["n_box"]) == ((11, 12), 5, 601, 20)
+        cs, xs = g["ch_step"], g["ctx_step"]
+        _check("sd15 vs reference fixture ctx", ctx[:, :, ::xs], g["ctx"], yc[:, :, ::xs])
+        _check("sd15 vs reference fixture down[0]", down[0][:, ::cs], g["down0"], yd[0][:, ::cs])
+        _check("sd15 vs reference fixture down[11]", down[11][:, ::cs], g["down11"], yd[11][:, ::cs])
+        _check("sd15 vs reference fixture mid", mid[:, ::cs], g["mid"], ym[:, ::cs])
+        _check("sd15 vs reference fixture eps", eps, g["eps"], ye)
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("workload", ["full", "cam"])
+def test_sd15_three_step_cfg_loop_vs_fp32_oracle(cuda_lib, workload):
+    """The configuration bench.py times — SD-1.5 size, CFG 2.0 (V = 12), CUDA graph + ControlNet/UNet two-stream overlap,
+    per-slot split-K scratch — run for 3 DDIM steps on both bench workloads (configs[2] full conditioning; configs[1]
+    bboxes_3d_data=None + zero map) against the fp32 oracle loop, with the reference arithmetic in bf16 as yardstick."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from magicdrive_b200.synthetic import synthetic_inputs
+    ucfg, ccfg = arch.UNetConfig(), arch.ControlNetConfig()
+    usd = arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), 11)
+    csd = arch.synthetic_state_dict(arch.controlnet_param_shapes(ccfg), 12)
+    un, cn = _models(ucfg, ccfg, usd, csd, torch.bfloat16)
+    inp = synthetic_inputs(1, 6, 28, 50, n_box=20 if workload == "full" else 0, map_hw=200, seed=0)
+    if workload == "cam":
+        inp["bev_map"] = torch.zeros_like(inp["bev_map"])
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=True, overlap_controlnet=True)
+    out = pipe(image=inp["bev_map"], camera_param=inp["camera_param"], prompt_embeds=inp["prompt_embeds"],
+               negative_prompt_embeds=inp["negative_prompt_embeds"], latents=inp["latents"], num_inference_steps=3,
+               guidance_scale=2.0, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
+    di = to_dev(inp, DEV)
+
+    def loop(usd_, csd_, dt):
+        d = to_dev(di, DEV, dt)
+        return O.denoise_loop(usd_, csd_, ucfg, ccfg, d["latents"], d["prompt_embeds"], d["negative_prompt_embeds"],
+                              d["camera_param"], d["bboxes_3d_data"], d["bev_map"], 3, 2.0)
+    truth = loop({k: v.to(DEV) for k, v in usd.items()}, {k: v.to(DEV) for k, v in csd.items()}, torch.float32)
+    yard = _bf16_yardstick(loop, usd, csd)
+    assert out.shape == truth.shape
+    _check(f"sd15 3-step CFG loop ({workload}, graph + overlap)", out, truth, yard)
+    assert (out[:, 0] - out[:, 1]).abs().max() > 1e-3
 
 
 def _tiny_case(scenes, n_box, seed, masks_off=False):
@@ -173,7 +217,7 @@ def test_tiny_pipeline_edge_cases_vs_oracle(cuda_lib, case):
                    guidance_scale=guidance, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
         assert out.shape == truth.shape
         e = rel_l2(out, truth)
-        print(f"[parity] edge case {case}[{k}]: rel-L2 {e:.3e} max-rel {max_rel(out, truth):.3e}")
+        record(f"[parity] edge case {case}[{k}]: rel-L2 {e:.3e} max-rel {max_rel(out, truth):.3e}")
         assert e < 2e-2
 
 
@@ -182,8 +226,8 @@ def test_view_sharded_cross_view_attention_two_gpus():
     """Cameras split across 2 GPUs, cross-view K/V all-gathered over NCCL, vs the single-GPU path (tools/check_view_shard.py)."""
     import subprocess
     import sys
-    if torch.cuda.device_count() < 2 or os.environ.get("MDB_TEST_MULTI_GPU") != "1":
-        pytest.skip("needs 2 GPUs and MDB_TEST_MULTI_GPU=1 (spawns torchrun; last run: profiles/view_shard_r1.txt)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 visible GPUs (spawns torchrun; last run: profiles/view_shard_r1.txt)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_view_shard.py")],

@@ -147,6 +147,35 @@ def test_oracle_reproduces_reference_forward_fixture():
 
 
 @torch.no_grad()
+def test_oracle_reproduces_reference_sd15_size_fixture():
+    """The oracle at the size the benchmark runs (SD-1.5 config: 4 levels, head dims 40 / 80 / 160, 6 views, 20 boxes,
+    200x200 BEV map) against the reference's own forward (oracle/make_golden_sd15.py): pins the full-size structure
+    (arch.py is shared between oracle and product, so a structural error common to both would otherwise pass)."""
+    from magicdrive_b200.synthetic import synthetic_inputs
+    g = golden("sd15_forward.pt")
+    ucfg, ccfg = arch.UNetConfig(), arch.ControlNetConfig(map_size=(8, g["map_hw"], g["map_hw"]))
+    usd = arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), g["seeds"][0])
+    csd = arch.synthetic_state_dict(arch.controlnet_param_shapes(ccfg), g["seeds"][1])
+    s, n, h, w = g["shape"]
+    inp = synthetic_inputs(s, n, h, w, n_box=g["n_box"], map_hw=g["map_hw"], seed=g["input_seed"])
+    lat5 = torch.stack([inp["latents"]] * n, 1)
+    t = torch.tensor([g["t"]])
+    down, mid, ctx = O.controlnet_forward(csd, ccfg, lat5, t, inp["camera_param"], inp["bboxes_3d_data"],
+                                          inp["prompt_embeds"], inp["bev_map"])
+    eps = O.unet_forward(usd, ucfg, lat5.reshape(-1, 4, h, w), t[0], ctx, down, mid)
+    cs, xs = g["ch_step"], g["ctx_step"]
+    assert len(down) == g["n_down"]
+    for d, nrm in zip(down, g["down_norms"]):
+        assert abs(float(d.norm()) - nrm) <= 2e-4 * nrm
+    # the north star's literal tolerance (rtol 1e-3 / atol 1e-4), met by the fp32 oracle at every tap
+    assert torch.allclose(ctx[:, :, ::xs], g["ctx"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(down[0][:, ::cs], g["down0"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(down[11][:, ::cs], g["down11"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(mid[:, ::cs], g["mid"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(eps, g["eps"], rtol=1e-3, atol=1e-4), (eps - g["eps"]).abs().max()
+
+
+@torch.no_grad()
 def test_oracle_reproduces_reference_pipeline_fixture():
     p = golden("tiny_pipeline.pt")
     ucfg, ccfg = tiny_configs()

@@ -79,7 +79,8 @@ def test_scene_step_time_vs_torch_eager_reference_arithmetic(cuda_lib, monkeypat
         eu, ec = eps.chunk(2)
         return eu + 2.0 * (ec - eu)
     ms_ref = _ms(reference, 5)
-    print(f"[speed] 6-view 224x400 CFG scene-step on this GPU: ours {ms_ours:.2f} ms ({1e3 / ms_ours:.1f} scene-steps/s), "
+    from tests.common import record
+    record(f"[speed] 6-view 224x400 CFG scene-step on this GPU: ours {ms_ours:.2f} ms ({1e3 / ms_ours:.1f} scene-steps/s), "
           f"reference arithmetic on torch bf16 kernels (eager, SDPA) {ms_ref:.2f} ms ({1e3 / ms_ref:.1f} scene-steps/s), "
           f"ratio {ms_ref / ms_ours:.2f}x")
     assert ms_ours < ms_ref

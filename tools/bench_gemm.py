@@ -44,6 +44,7 @@ ap.add_argument("--debug-flags", type=int, default=0)
 ap.add_argument("--bn", type=int, default=0)
 ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--trace", action="store_true", help="print per-CTA clock64 phase stamps of the persistent kernel")
+ap.add_argument("--warm", action="store_true", help="no L2 flush between reps: operands L2-resident, like activations inside a step")
 ap.add_argument("--profile", action="store_true", help="one launch per shape between cudaProfilerStart/Stop (for ncu)")
 args = ap.parse_args()
 dev = "cuda"
@@ -66,6 +67,22 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
     for _ in range(3):
         ops.gemm_conv(x, wt, **kw)
     torch.cuda.synchronize()
+    if args.trace and (args.variant or int(os.environ.get("MDB_GEMM_VARIANT", "0"))) in (3, 4):
+        tr = torch.zeros(160 * 16, dtype=torch.int64, device=dev)
+        if not args.warm:
+            flush.zero_()
+        ops.gemm_conv(x, wt, trace=tr, **kw)
+        torch.cuda.synchronize()
+        tr = tr.view(160, 16).cpu()
+        live = [i for i in range(160) if tr[i, 0] != 0]
+        t0 = min(int(tr[i, 0]) for i in live)
+        names = ["entry", "setup", "tma_end", "mma_end", "aux_stores_issued", "aux_drained", "epi_end", "mma_tile0", "epi_tile0",
+                 "pre_sync", "exit"]
+        print(f"{name}: {len(live)} CTAs; ns since the first CTA's entry; kernel span {max(int(tr[i, 10]) for i in live) - t0} ns")
+        dur = sorted(live, key=lambda i: int(tr[i, 10]))
+        for cta in [live[0], live[1], dur[len(dur) // 2], dur[-2], dur[-1]]:
+            print(f"   cta {cta:3d}: " + " ".join(f"{n}={int(tr[cta, i]) - t0 if tr[cta, i] else -1}" for i, n in enumerate(names)))
+        continue
     if args.trace:
         tr = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
         flush.zero_()
@@ -87,7 +104,8 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
         continue
     tot = 0.0
     for _ in range(args.reps):
-        flush.zero_()
+        if not args.warm:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.gemm_conv(x, wt, **kw)

@@ -15,4 +15,6 @@ MDB_GEMM_VARIANT=4 timeout 200 python tools/bench_gemm.py > gpurun_out/s1/gemm_t
 MDB_GEMM_VARIANT=3 timeout 200 python tools/bench_gemm.py > gpurun_out/s1/gemm_times_pair.log 2>&1
 MDB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zzz_experimental_gpu.py -q -m gpu -x -k "attention" 2>&1 | tail -15 > gpurun_out/s1/experimental_attn.log
 timeout 120 python tools/bench_attn.py tc3 tc2 > gpurun_out/s1/bench_attn_tc3.log 2>&1
+MDB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zzz_experimental_gpu.py -q -m gpu -x -k "groupnorm" 2>&1 | tail -15 > gpurun_out/s1/experimental_gn.log
+timeout 120 python tools/bench_norm.py > gpurun_out/s1/bench_norm.log 2>&1
 tail -n 30 gpurun_out/s1/*.log
