@@ -127,6 +127,11 @@ int mdb_softmax_rows(const float* s, int lds, long long rows, int cols, void* ou
 int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
                   int b_kv, int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale, void* stream);
 
+/* Debug hook (NULL in production): a device int64[3 * 16 * 8] buffer that receives clock64 stamps of the first CTA of
+ * every following fused-attention launch (MMA warp and two softmax warps, 16 KV iterations, 8 points each);
+ * tools/bench_attn.py --trace prints them.  Pass NULL to switch it off. */
+int mdb_attention_debug_trace(void* device_i64_384);
+
 /* out = a + b (bf16), n elements (unet_2d_condition_multiview.py:464-473, 487-488). */
 int mdb_add(const void* a, const void* b, void* out, long long n, void* stream);
 

@@ -43,6 +43,12 @@ class UNetConfig:
     def n_cam(self):
         return len(self.neighboring_view_pair)
 
+    @property
+    def multiview(self) -> bool:
+        """False (no neighbouring_view_pair) = the stock diffusers UNet2DConditionModel: BasicTransformerBlock without the
+        cross-view attention (BASELINE.json configs[0]: 1-view SD-1.5 UNet, text-only conditioning)."""
+        return len(self.neighboring_view_pair) > 0
+
 
 @dataclass
 class ControlNetConfig:
@@ -160,7 +166,7 @@ def up_blocks(cfg: UNetConfig) -> List[BlockSpec]:
             rs = ResnetSpec(f"up_blocks.{i}.resnets.{j}", run_c + skip_c, out_c, skip_c=skip_c)
             tr = None
             if typ == "CrossAttnUpBlock2D":
-                tr = TransformerSpec(f"up_blocks.{i}.attentions.{j}", out_c, rev_heads[i], True)
+                tr = TransformerSpec(f"up_blocks.{i}.attentions.{j}", out_c, rev_heads[i], cfg.multiview)
             layers.append((rs, tr))
         samp = None if final else SamplerSpec(f"up_blocks.{i}.upsamplers.0.conv", out_c, "up")
         blocks.append(BlockSpec(f"up_blocks.{i}", layers, samp))
@@ -242,7 +248,7 @@ def _encoder_shapes(sh, cfg, multiview):
 
 def unet_param_shapes(cfg: UNetConfig) -> "OrderedDict[str, tuple]":
     sh = OrderedDict()
-    _encoder_shapes(sh, cfg, True)
+    _encoder_shapes(sh, cfg, cfg.multiview)
     temb = cfg.time_embed_dim
     for blk in up_blocks(cfg):
         for rs, tr in blk.layers:

@@ -25,6 +25,7 @@ struct AttnTcParams {
   const int* kv_index;
   int n_sets;
   float scale_log2;
+  long long* trace;  // debug (mdb_attention_debug_trace): clock64 stamps of CTA (0,0,0): [3 warps][16 iterations][8 points]
 };
 
 template <int D>

@@ -71,6 +71,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * ATT_BM;
   const int ntiles = (p.lk + ATT_BN - 1) / ATT_BN;
   const int total_iters = ntiles * p.n_sets;
+  long long* const trace = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.trace : nullptr;
+#define MDB_ATRACE(slot, it_, k)                                                       \
+  do {                                                                                 \
+    if (trace && lane == 0 && (it_) < 16) trace[((slot) * 16 + (it_)) * 8 + (k)] = clock64(); \
+  } while (0)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
@@ -155,7 +160,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     int j = 0, set = 0;
     for (int it = 0; it < total_iters; ++it) {
       const int s = it % NBUF, st = it % STAGES;
+      MDB_ATRACE(0, it, 0);
       mbar_wait(&p_full[s], static_cast<uint32_t>(it / NBUF) & 1u);  // P_it written, S_it no longer read
+      MDB_ATRACE(0, it, 1);
       if (j == 0 && set > 0) mbar_wait(o_free, static_cast<uint32_t>(set - 1) & 1u);  // previous set's O has been read
       tc_fence_after();
       if (elect_one()) {
@@ -173,8 +180,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (j == ntiles - 1) umma_commit(o_full);
       }
       __syncwarp();
+      MDB_ATRACE(0, it, 2);
       // S_{it+NBUF} reuses buffer s: tcgen05.mma of one CTA execute in issue order, so it starts after PV_it has read P_it
       if (it + NBUF < total_iters) issue_qk(it + NBUF);
+      MDB_ATRACE(0, it, 3);
       if (++j == ntiles) {
         j = 0;
         ++set;
@@ -198,12 +207,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < ntiles; ++j, ++it) {
         const int s = it % NBUF;
         const uint32_t tmem_s = lane_base + static_cast<uint32_t>(s * ATT_BN + hlf * 64);
+        const int tslot = (warp == 2) ? 1 : ((warp == 6) ? 2 : -1);
+        if (tslot > 0) MDB_ATRACE(tslot, it, 0);
         mbar_wait(&s_full[s], static_cast<uint32_t>(it / NBUF) & 1u);
         tc_fence_after();
+        if (tslot > 0) MDB_ATRACE(tslot, it, 1);
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(tmem_s, v0);
         tmem_ld_32x32(tmem_s + 32, v1);
         tmem_ld_wait();
+        if (tslot > 0) MDB_ATRACE(tslot, it, 2);
         const int nval = p.lk - (j * ATT_BN + hlf * 64);  // valid keys among this thread's 64 columns
         const bool tail = nval < 64;
         float mx = -INFINITY;
@@ -219,6 +232,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (32 + i < nval) mx = fmaxf(mx, __uint_as_float(v1[i]));
           }
         }
+        if (tslot > 0) MDB_ATRACE(tslot, it, 3);
         const float m_new = mx * sc;  // sc > 0; -inf when this half has no valid key in the tile
         const bool need = m_new > m_ref + ATT_LAZY_LOG2;
         if (__any_sync(0xffffffffu, need)) {
@@ -267,13 +281,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             pk[16 + (i >> 1)] = pack_bf16(p2, p3);
           }
         }
+        if (tslot > 0) MDB_ATRACE(tslot, it, 4);
         tmem_st_32x16(tmem_s, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
         tmem_st_32x16(tmem_s + 16, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16]));
         tmem_st_wait();
+        if (tslot > 0) MDB_ATRACE(tslot, it, 5);
         l += rs;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (tslot > 0) MDB_ATRACE(tslot, it, 6);
       }
       // ---- end of the KV set: combine the two split-KV halves, normalise, store
       mbar_wait(o_full, static_cast<uint32_t>(set) & 1u);
@@ -320,6 +337,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   }
 
+#undef MDB_ATRACE
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();

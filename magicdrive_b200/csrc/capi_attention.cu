@@ -19,6 +19,8 @@
 #include "attention_tc2.cuh"
 #include "attention_tc3.cuh"
 
+static long long* g_attn_trace = nullptr;  // debug: device int64[3*16*8] for attention_tc2's phase stamps (mdb_attention_debug_trace)
+
 namespace {
 
 constexpr int BM = 64;   // queries per CTA (16 per warp)
@@ -311,6 +313,7 @@ int launch_attention_tc(const void* q, int ldq, const void* k, int ldk, const vo
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo, p.lq = lq, p.lk = lk, p.kv_index = kv_index, p.n_sets = n_sets;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   dim3 grid((lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
   cudaError_t le = mdb::launch_pdl(mdb::attention_tc_kernel<D>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tq, tk, tv, p);
   if (le != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc_kernel launch: %s", cudaGetErrorString(le));
@@ -339,6 +342,7 @@ int launch_attention_tc2(const void* q, int ldq, const void* k, int ldk, const v
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo, p.lq = lq, p.lk = lk, p.kv_index = kv_index, p.n_sets = n_sets;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   dim3 grid((lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
   cudaError_t le = mdb::launch_pdl(mdb::attention_tc2_kernel<D, DOUBLE_S>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tq, tk, tv, p);
   if (le != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "attention_tc2_kernel launch: %s", cudaGetErrorString(le));
@@ -448,4 +452,9 @@ extern "C" int mdb_attention(const void* q, int ldq, const void* k, int ldk, con
     case 64: return launch_attention<64>(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, lq, lk, kv_index, n_sets, scale, st);
     default: return set_error(MDB_ERR_UNSUPPORTED, "mdb_attention: head dim %d not instantiated (8,16,32,40,64,80,160)", d);
   }
+}
+
+extern "C" int mdb_attention_debug_trace(void* device_i64_384) {
+  g_attn_trace = static_cast<long long*>(device_i64_384);
+  return MDB_OK;
 }

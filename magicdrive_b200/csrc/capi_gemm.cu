@@ -330,7 +330,7 @@ extern "C" int mdb_gemm_conv_stats_parts(const mdb_gemm_desc* d) {
   if (k == 0) return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv_stats_parts: this descriptor runs on the split-K kernel, which emits no row statistics");
   Plan3 p3;
   make_plan3(d, k, &p3);
-  return 2 * p3.n_tiles;
+  return MDB_EPI_GROUPS * p3.n_tiles;
 }
 
 extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {

@@ -36,16 +36,80 @@ struct GemmParams3 {
   float ln_inv_c, ln_eps;
   const float* ln_colsum;  // [n_out] sum_k W'[n, k]
   // row statistics of this GEMM's bf16 output (producer side)
-  float* stats_out;        // [pixels][2 * n_tiles][2] or nullptr
+  float* stats_out;        // [pixels][n_tiles * kEpiGroups][2] or nullptr
 };
+
+#ifndef MDB_EPI_GROUPS
+#define MDB_EPI_GROUPS 4
+#endif
+
+// ---- fp32 pairs in 64-bit registers: FFMA2 / FADD2 / FMUL2 (sm_100) halve the epilogue's instruction count
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long pk2u(uint32_t a, uint32_t b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long r, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long bf2_to_f2(uint32_t r) { return pk2u(r << 16, r & 0xffff0000u); }
+__device__ __forceinline__ uint32_t f2_to_bf2(unsigned long long v) {
+  float a, b;
+  upk2(v, a, b);
+  return pack_bf16(a, b);
+}
+// gelu_erf (gemm_tc.cuh) on a pair: the polynomial and the products run as packed ops, rcp / ex2 per element.
+__device__ __forceinline__ unsigned long long gelu_erf2(unsigned long long x2) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  const unsigned long long ax2 = mul2(pk2(fabsf(x0), fabsf(x1)), pk2(0.70710678118654752440f, 0.70710678118654752440f));
+  float d0, d1, t0, t1, a0, a1, e0, e1;
+  upk2(fma2(pk2(0.3275911f, 0.3275911f), ax2, pk2(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const unsigned long long t2 = pk2(t0, t1);
+  // -(a1 t + a2 t^2 + ... + a5 t^5): coefficients negated so that erf = 1 + npoly * e
+  unsigned long long np = fma2(t2, pk2(-1.061405429f, -1.061405429f), pk2(1.453152027f, 1.453152027f));
+  np = fma2(np, t2, pk2(-1.421413741f, -1.421413741f));
+  np = fma2(np, t2, pk2(0.284496736f, 0.284496736f));
+  np = fma2(np, t2, pk2(-0.254829592f, -0.254829592f));
+  np = mul2(np, t2);
+  upk2(mul2(mul2(ax2, ax2), pk2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  float r0, r1;
+  upk2(fma2(np, pk2(e0, e1), pk2(1.0f, 1.0f)), r0, r1);  // erf(|x| / sqrt 2)
+  const unsigned long long hx2 = mul2(x2, pk2(0.5f, 0.5f));
+  return fma2(hx2, pk2(copysignf(r0, x0), copysignf(r1, x1)), hx2);
+}
 
 template <int BLOCK_N, int CTAS>
 struct PairCfg {
   static constexpr int kBRows = BLOCK_N / CTAS;
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kNBuf = 6;               // 128-row x 32-column (64 B) staging boxes: residual in, result out
-  static constexpr int kAhead = 3;              // how many chunks ahead of the store cursor buffers are prepared
+  static constexpr int kNBuf = 7;               // 128-row x 32-column (64 B) staging boxes: residual in, result out
+  static constexpr int kAhead = 4;              // how many chunks ahead of the store cursor buffers are prepared
   static constexpr int kBufBytes = 128 * 64;
   static constexpr int kConstBytes = 2 * 2 * 256 * 4;  // [acc stage][bias+shift | colsum][BLOCK_N] fp32
   static constexpr int kBarBytes = 1024;
@@ -54,7 +118,8 @@ struct PairCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStride = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128) ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiGroups = MDB_EPI_GROUPS;  // groups of four epilogue warps (one warp per TMEM lane quarter)
+  static constexpr int kEpiWarps = 4 * kEpiGroups;
   static constexpr int kThreads = 96 + 32 * kEpiWarps;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNBuf * kBufBytes + kConstBytes + kBarBytes + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -290,9 +355,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // =========================== epilogue (warps 3..10) ===========================
+    // =========================== epilogue (warps 3 .. 3 + 4 G) ===========================
+    // G groups of four warps (one per TMEM lane quarter); group g owns the 32-column chunks c with c % G == g.  All
+    // arithmetic on fp32 PAIRS (FFMA2 / FADD2 / FMUL2): out = A_row * acc + (B_row * colsum_n + bias_n) [+ residual] with
+    // A_row = rstd * scale, B_row = -mean * rstd * scale (folded LayerNorm) or A_row = scale, B_row = 0.
+    constexpr int G = Cfg::kEpiGroups;
+    constexpr int NEPI = 128 * G;
     const int q = warp & 3;
-    const int eg = (warp - 3) >> 2;  // which of the two interleaved chunk sets this warp owns
+    const int eg = (warp - 3) >> 2;
     const int etid = threadIdx.x - 96;
     const int row = q * 32 + lane;
     const int box_hw = p.bh * p.bw;
@@ -300,133 +370,162 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int rem = row - li * box_hw;
     const int lh = rem / p.bw;
     const int lw = rem - lh * p.bw;
-    const uint32_t smO_u32 = smem_u32(smO);
+    uint8_t* const my_row = smO + row * 64;         // this thread's 64-byte row inside a staging box
+    const int swz = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk j sits at j ^ swz
     const bool has_ln = pp.ln_stats != nullptr;
+    const float scale = p.out_scale;
+    // per-tile constants (bias + per-image shift, folded-LayerNorm column sums) are fetched one tile ahead
+    auto tile_coords = [&](int t, int& nt, int& mt, int& tn, int& th, int& tw) {
+      const int mg = t % pp.m_groups;
+      nt = t / pp.m_groups;
+      mt = mg * CTAS + static_cast<int>(rank);
+      tw = mt % p.tiles_w;
+      th = (mt / p.tiles_w) % p.tiles_h;
+      tn = mt / (p.tiles_w * p.tiles_h);
+    };
+    auto fetch_consts = [&](int t, float& b, float& cs) {
+      b = 0.f, cs = 0.f;
+      if (etid < BLOCK_N && t < total) {
+        int nt, mt, tn, th, tw;
+        tile_coords(t, nt, mt, tn, th, tw);
+        const int n = nt * BLOCK_N + etid;
+        if (n < p.n_out) {
+          const int img_tile = min(tn * p.bn, p.n_img - 1);  // one image per tile whenever a per-image shift is used (host check)
+          if (p.bias) b = __ldg(p.bias + n);
+          if (p.rowbias) b += __ldg(p.rowbias + static_cast<long long>(img_tile) * p.rowbias_ld + n);
+          b *= scale;
+          if (has_ln) cs = __ldg(pp.ln_colsum + n);
+        }
+      }
+    };
+    auto row_pix = [&](int t, bool& ok) {
+      int nt, mt, tn, th, tw;
+      tile_coords(t, nt, mt, tn, th, tw);
+      const int img = tn * p.bn + li, oh = th * p.bh + lh, ow = tw * p.bw + lw;
+      ok = (t < total) && (mt < pp.m_tiles) && (li < p.bn) && (img < p.n_img) && (oh < p.h_out) && (ow < p.w_out);
+      return (static_cast<long long>(img) * p.h_out + oh) * p.w_out + ow;
+    };
+    constexpr int PF = 4;  // LayerNorm row-statistics partials fetched one tile ahead (the rest, if any, at use)
+    float2 pf[PF];
+    auto fetch_stats = [&](int t) {
+#pragma unroll
+      for (int j = 0; j < PF; ++j) pf[j] = make_float2(0.f, 0.f);
+      bool ok;
+      const long long pix = row_pix(t, ok);
+      if (has_ln && ok) {
+        const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + pix * pp.ln_parts;
+#pragma unroll
+        for (int j = 0; j < PF; ++j)
+          if (j < pp.ln_parts) pf[j] = __ldg(sp + j);
+      }
+    };
+    float nb, ncs;
+    fetch_consts(cluster_id, nb, ncs);
+    fetch_stats(cluster_id);
+    if (etid < BLOCK_N) smC[etid] = nb, smC[256 + etid] = ncs;
     int it = 0;
     int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
     for (int t = cluster_id; t < total; t += n_clusters, ++it) {
-      const int mg = t % pp.m_groups;
-      const int nt = t / pp.m_groups;
-      const int mt = mg * CTAS + static_cast<int>(rank);
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int tn = mt / (p.tiles_w * p.tiles_h);
-      const int img = tn * p.bn + li, oh = th * p.bh + lh, ow = tw * p.bw + lw;
-      const int n0 = nt * BLOCK_N;
-      const bool row_ok = (mt < pp.m_tiles) && (li < p.bn) && (img < p.n_img) && (oh < p.h_out) && (ow < p.w_out);
-      const long long pix = (static_cast<long long>(img) * p.h_out + oh) * p.w_out + ow;
+      int nt, mt, tn, th, tw;
+      tile_coords(t, nt, mt, tn, th, tw);
+      bool row_ok;
+      const long long pix = row_pix(t, row_ok);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      // ---- per-tile constants: bias + per-image shift (and the folded LayerNorm's column sums) -> shared memory
-      float* cst = smC + as * 512;
-      {
-        const int img_tile = min(tn * p.bn, p.n_img - 1);  // one image per tile whenever a per-image shift is used (host check)
-        for (int j = etid; j < BLOCK_N; j += 32 * Cfg::kEpiWarps) {
-          const int n = n0 + j;
-          float b = 0.f, cs = 0.f;
-          if (n < p.n_out) {
-            if (p.bias) b = __ldg(p.bias + n);
-            if (p.rowbias) b += __ldg(p.rowbias + static_cast<long long>(img_tile) * p.rowbias_ld + n);
-            if (has_ln) cs = __ldg(pp.ln_colsum + n);
-          }
-          cst[j] = b;
-          cst[256 + j] = cs;
-        }
-      }
-      float mean = 0.f, rstd = 1.f;
-      if (has_ln && row_ok) {
-        const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + pix * pp.ln_parts;
+      const float* cst = smC + as * 512;
+      // this tile's row scalars from the prefetched statistics
+      float rowA = scale, rowB = 0.f;
+      if (has_ln) {
         float s = 0.f, ss = 0.f;
-        for (int j = 0; j < pp.ln_parts; ++j) {
-          const float2 v = __ldg(sp + j);
-          s += v.x;
-          ss += v.y;
+#pragma unroll
+        for (int j = 0; j < PF; ++j) s += pf[j].x, ss += pf[j].y;
+        if (row_ok) {
+          const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + pix * pp.ln_parts;
+          for (int j = PF; j < pp.ln_parts; ++j) {
+            const float2 v = __ldg(sp + j);
+            s += v.x, ss += v.y;
+          }
         }
-        mean = s * pp.ln_inv_c;
-        const float var = fmaxf(ss * pp.ln_inv_c - mean * mean, 0.f);
-        rstd = rsqrtf(var + pp.ln_eps);
+        const float mean = s * pp.ln_inv_c;
+        const float rstd = rsqrtf(fmaxf(ss * pp.ln_inv_c - mean * mean, 0.f) + pp.ln_eps);
+        rowA = rstd * scale;
+        rowB = -mean * rowA;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::kEpiWarps) : "memory");  // constants visible to all epilogue warps
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // constants of this tile visible; everyone left the previous tile
+      // next tile's constants / statistics: loads in flight while this tile is processed
+      fetch_consts(t + n_clusters, nb, ncs);
+      fetch_stats(t + n_clusters);
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       const int left = (pp.out_cols - nt * out_per_tile) / 32;
       const int nch = left < ch_tile ? left : ch_tile;
-      float st_s = 0.f, st_ss = 0.f;
+      const unsigned long long A2 = pk2(rowA, rowA), B2 = pk2(rowB, rowB);
+      unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
 
       for (int c = 0; c < nch; ++c, ++gk) {
-        if ((c & 1) != eg) continue;
+        if ((c % G) != eg) continue;
         const int buf = gk % NBUF;
-        mbar_wait(&res_full[buf], (gk / NBUF) & 1);
-        const uint32_t sbuf = smO_u32 + buf * Cfg::kBufBytes;
+        uint8_t* const srow = my_row + buf * Cfg::kBufBytes;
         if (!geglu) {
           uint32_t v[32];
-          tmem_ld_32x32(lane_addr + c * 32, v);
+          tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while we wait for the staging box
+          mbar_wait(&res_full[buf], (gk / NBUF) & 1);
+          const float4* cb4 = reinterpret_cast<const float4*>(cst + c * 32);
           tmem_ld_wait();
-          const float* cb = cst + c * 32;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+            const float4 b0 = cb4[2 * j], b1 = cb4[2 * j + 1];
+            unsigned long long t0 = pk2(b0.x, b0.y), t1 = pk2(b0.z, b0.w), t2 = pk2(b1.x, b1.y), t3 = pk2(b1.z, b1.w);
             if (has_ln) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = rstd * (f[e] - mean * cb[256 + 8 * j + e]);
+              const float4 s0 = cb4[64 + 2 * j], s1 = cb4[64 + 2 * j + 1];
+              t0 = fma2(B2, pk2(s0.x, s0.y), t0), t1 = fma2(B2, pk2(s0.z, s0.w), t1);
+              t2 = fma2(B2, pk2(s1.x, s1.y), t2), t3 = fma2(B2, pk2(s1.z, s1.w), t3);
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = (f[e] + cb[8 * j + e]) * p.out_scale;
+            unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), t0), o1 = fma2(A2, pk2u(v[8 * j + 2], v[8 * j + 3]), t1);
+            unsigned long long o2 = fma2(A2, pk2u(v[8 * j + 4], v[8 * j + 5]), t2), o3 = fma2(A2, pk2u(v[8 * j + 6], v[8 * j + 7]), t3);
+            uint4* const slot = reinterpret_cast<uint4*>(srow + ((j ^ swz) << 4));
             if (pp.use_res_tma) {
-              const uint4 r = ld_shared_v4(sbuf + stage_off(row, j));
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 rf = __bfloat1622float2(rh[e]);
-                f[2 * e] += rf.x;
-                f[2 * e + 1] += rf.y;
-              }
+              const uint4 r = *slot;
+              o0 = add2(o0, bf2_to_f2(r.x)), o1 = add2(o1, bf2_to_f2(r.y)), o2 = add2(o2, bf2_to_f2(r.z)), o3 = add2(o3, bf2_to_f2(r.w));
             }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]), o.y = pack_bf16(f[2], f[3]), o.z = pack_bf16(f[4], f[5]), o.w = pack_bf16(f[6], f[7]);
-            if (pp.stats_out) {  // statistics of the values the consumer will actually read (bf16-rounded)
-              const __nv_bfloat162* oh2 = reinterpret_cast<const __nv_bfloat162*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 of = __bfloat1622float2(oh2[e]);
-                st_s += of.x + of.y;
-                st_ss = fmaf(of.x, of.x, fmaf(of.y, of.y, st_ss));
-              }
+            if (pp.stats_out) {
+              st_s2 = add2(add2(st_s2, add2(o0, o1)), add2(o2, o3));
+              st_ss2 = fma2(o0, o0, fma2(o1, o1, fma2(o2, o2, fma2(o3, o3, st_ss2))));
             }
-            st_shared_v4(sbuf + stage_off(row, j), o);
+            *slot = make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3));
           }
         } else {
           constexpr int HALF = BLOCK_N / 2;
-          const float* cbv = cst + c * 32;
-          const float* cbg = cst + HALF + c * 32;
+          mbar_wait(&res_full[buf], (gk / NBUF) & 1);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t v[16], g[16];
             tmem_ld_32x16(lane_addr + c * 32 + hh * 16, v);
             tmem_ld_32x16(lane_addr + HALF + c * 32 + hh * 16, g);
+            const float4* cv4 = reinterpret_cast<const float4*>(cst + c * 32 + hh * 16);
+            const float4* cg4 = reinterpret_cast<const float4*>(cst + HALF + c * 32 + hh * 16);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              float o8[8];
+              unsigned long long o[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int cc = hh * 16 + j * 8 + e;
-                float a = __uint_as_float(v[j * 8 + e]);
-                float gg = __uint_as_float(g[j * 8 + e]);
+              for (int e = 0; e < 2; ++e) {
+                const float4 bv = cv4[2 * j + e], bg = cg4[2 * j + e];
+                unsigned long long tv0 = pk2(bv.x, bv.y), tv1 = pk2(bv.z, bv.w), tg0 = pk2(bg.x, bg.y), tg1 = pk2(bg.z, bg.w);
                 if (has_ln) {
-                  a = rstd * (a - mean * cbv[256 + cc]);
-                  gg = rstd * (gg - mean * cbg[256 + cc]);
+                  const float4 sv = cv4[64 + 2 * j + e], sg = cg4[64 + 2 * j + e];
+                  tv0 = fma2(B2, pk2(sv.x, sv.y), tv0), tv1 = fma2(B2, pk2(sv.z, sv.w), tv1);
+                  tg0 = fma2(B2, pk2(sg.x, sg.y), tg0), tg1 = fma2(B2, pk2(sg.z, sg.w), tg1);
                 }
-                a += cbv[cc];
-                gg += cbg[cc];
-                o8[e] = a * gelu_erf(gg);
+                const int k = 8 * j + 4 * e;
+                const unsigned long long a0 = fma2(A2, pk2u(v[k], v[k + 1]), tv0), a1 = fma2(A2, pk2u(v[k + 2], v[k + 3]), tv1);
+                const unsigned long long g0 = fma2(A2, pk2u(g[k], g[k + 1]), tg0), g1 = fma2(A2, pk2u(g[k + 2], g[k + 3]), tg1);
+                o[2 * e] = mul2(a0, gelu_erf2(g0));
+                o[2 * e + 1] = mul2(a1, gelu_erf2(g1));
               }
-              uint4 o;
-              o.x = pack_bf16(o8[0], o8[1]), o.y = pack_bf16(o8[2], o8[3]), o.z = pack_bf16(o8[4], o8[5]), o.w = pack_bf16(o8[6], o8[7]);
-              st_shared_v4(sbuf + stage_off(row, hh * 2 + j), o);
+              *reinterpret_cast<uint4*>(srow + (((hh * 2 + j) ^ swz) << 4)) =
+                  make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3]));
             }
           }
         }
@@ -434,14 +533,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&out_ready[buf]);
       }
-      if (pp.stats_out && row_ok)
-        reinterpret_cast<float2*>(pp.stats_out)[(pix * pp.n_tiles + nt) * 2 + eg] = make_float2(st_s, st_ss);
+      if (pp.stats_out && row_ok) {
+        float s0, s1, q0, q1;
+        upk2(st_s2, s0, s1);
+        upk2(st_ss2, q0, q1);
+        // one slot per (N tile, epilogue group): [pix][n_tiles][G]
+        reinterpret_cast<float2*>(pp.stats_out)[(pix * pp.n_tiles + nt) * G + eg] = make_float2(s0 + s1, q0 + q1);
+      }
       // release this accumulator stage to the MMA warp of the leader CTA
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
         else mbar_arrive(&acc_empty[as]);
+      }
+      // publish the next tile's constants (buffer of the other accumulator stage: nobody reads it any more, see bar.sync)
+      if (etid < BLOCK_N) {
+        float* nx = smC + (as ^ 1) * 512;
+        nx[etid] = nb, nx[256 + etid] = ncs;
       }
       if (warp == 3 && lane == 0 && it == 0) MDB_TRACE3(8);
     }

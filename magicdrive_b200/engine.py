@@ -340,7 +340,7 @@ class UNetEngine(_Net):
     """UNet2DConditionModelMultiview.forward on the GPU (unet_2d_condition_multiview.py:327-527)."""
 
     def __init__(self, cfg: arch.UNetConfig, sd, device):
-        super().__init__(cfg, sd, device, multiview=True)
+        super().__init__(cfg, sd, device, multiview=cfg.multiview)
         self.up = arch.up_blocks(cfg)
         self.resnets += [rs for b in self.up for rs, _ in b.layers]
         self.transformers += [tr for b in self.up for _, tr in b.layers if tr]

@@ -180,6 +180,12 @@ class UNet2DConditionModelMultiview(_B200Module):
                 raise ValueError(f"UNet2DConditionModelMultiview (B200): unsupported config {k}={extra[k]!r}")
         self._init_common(cfg, arch.unet_param_shapes(cfg), extra)
 
+    @classmethod
+    def stock_unet(cls, **kwargs):
+        """The plain diffusers UNet2DConditionModel (unet_2d_condition.py:161-505) on the same engine: no cross-view attention,
+        any batch size (BASELINE.json configs[0]: 1-view SD-1.5 UNet, text-only conditioning)."""
+        return cls(neighboring_view_pair={}, **kwargs)
+
     def engine(self) -> UNetEngine:
         return self._get_engine(UNetEngine)
 
@@ -205,7 +211,7 @@ class UNet2DConditionModelMultiview(_B200Module):
             raise ValueError("attention_mask / class_labels / timestep_cond are not used by the MagicDrive path")
         eng = self._get_engine(UNetEngine)
         n, c, h, w = sample.shape
-        if n % self.arch_cfg.n_cam:
+        if self.arch_cfg.multiview and n % self.arch_cfg.n_cam:
             raise ValueError(f"batch {n} is not a multiple of the {self.arch_cfg.n_cam} camera views")
         ctx_kv, lc = self.prepare_context(encoder_hidden_states)
         x = ops.pack_latents(ops.nchw_to_nhwc(sample), UNetEngine.CIN_PAD)

@@ -161,13 +161,17 @@ class BEVControlNetDenoiser:
         self._graph = None
         self._graph_key = None
         self._graph_state = None
+        self._cond_graph = None        # CUDA graph of _encode_conditions on the resident state
+        self._cond_graph_state = None
         self._static = None
 
     def release_graph(self):
-        """Drop the captured CUDA graph (it is re-captured on the next run_steps)."""
+        """Drop the captured CUDA graphs (they are re-captured on the next use)."""
         self._graph = None
         self._graph_key = None
         self._graph_state = None
+        self._cond_graph = None
+        self._cond_graph_state = None
 
     def _side_stream(self, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -287,70 +291,102 @@ class BEVControlNetDenoiser:
             if conditional_latents is not None:
                 vb, ve = self.view_shard.views
                 conditional_latents = [row[vb:ve] for row in conditional_latents]
-        camera_param = camera_param.to(dev, F32)
+        # ---- assemble the guidance batch where the inputs live (normally the host: a few small tensors), [uncond ; cond]
+        camera_param = camera_param.to(F32)
         S, n_cam = camera_param.shape[:2]
-        prompt_embeds = prompt_embeds.to(dev, F32)
-        image = image.to(dev, F32)
-        boxes = None if bboxes_3d_data is None else {k: v.to(dev) for k, v in bboxes_3d_data.items()}
+        prompt_embeds = prompt_embeds.to(F32)
+        image = image.to(F32)
+        boxes = bboxes_3d_data
         if cfg:
-            negative_prompt_embeds = negative_prompt_embeds.to(dev, F32)
             # unconditional half of the BEV map: the scene's map, zeros on request (:296-300), or the ControlNet's
             # configured uncond map (add_uncond_to_kwargs -> substitute_with_uncond_map)
             uncond_image = torch.zeros_like(image) if use_zero_map_as_unconditional else image
             kw = cn.add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=boxes, image=uncond_image,
                                          max_len=bbox_max_length)
             camera_param, boxes = kw["camera_param"], kw["bboxes_3d_data"]
-            text = torch.cat([negative_prompt_embeds, prompt_embeds])
-            image = torch.cat([kw["image"], image])
+            text = torch.cat([negative_prompt_embeds.to(prompt_embeds), prompt_embeds])
+            image = torch.cat([kw["image"].to(image), image])
         else:
             text = prompt_embeds
-        cond = cn.prepare_conditions(camera_param, boxes, text, image)
-        u_kv, lc = un.prepare_context(cond["ctx"])
-        lat = latents.to(dev, F32)
+        lat = latents.to(F32)
         if lat.dim() == 4:
             lat = torch.stack([lat] * n_cam, dim=1)
         S_, _, c, h, w = lat.shape
         lat_nhwc = lat.reshape(S * n_cam, c, h, w).permute(0, 2, 3, 1).contiguous().view(-1, c)
         V = S * n_cam * (2 if cfg else 1)
+        lc = 1 + text.shape[1] + (0 if boxes is None else boxes["bboxes"].shape[2])
         pin_mode, pin_mask, pin_cond = None, None, None
         if conditional_latents is not None and any(c is not None for row in conditional_latents for c in row):
             if len(conditional_latents) != S or any(len(row) != n_cam for row in conditional_latents):
                 raise ValueError("conditional_latents must be a list[scenes] of list[n_cam] of (4, h, w) tensors or None")
             pin_mode = "change" if conditional_latents_change_every_input else "once"
-            pin_mask = torch.tensor([int(c is not None) for row in conditional_latents for c in row], dtype=torch.int32, device=dev)
+            pin_mask = torch.tensor([int(c is not None) for row in conditional_latents for c in row], dtype=torch.int32)
             pin_cond = torch.stack([torch.zeros(c, h, w) if x is None else x.to("cpu", F32)
                                     for row in conditional_latents for x in row])
-            pin_cond = pin_cond.to(dev).permute(0, 2, 3, 1).contiguous().view(-1, c)
-        # the resident state (and the captured graph) hold pointers into the engines' packed weights: a rebuilt engine
+            pin_cond = pin_cond.permute(0, 2, 3, 1).contiguous().view(-1, c)
+        inputs = dict(camera=camera_param, text=text, image=image, latents=lat_nhwc)
+        if boxes is not None:
+            inputs.update(bboxes=boxes["bboxes"].to(F32), classes=boxes["classes"], masks=boxes["masks"])
+        if pin_mode is not None:
+            inputs.update(pin_mask=pin_mask, pin_cond=pin_cond)
+        # the resident state (and the captured graphs) hold pointers into the engines' packed weights: a rebuilt engine
         # (load_state_dict, .to(), BEVControlNetModel.prepare) must invalidate both
-        sig = (V, h, w, cfg, lc, S, n_cam, pin_mode, id(un.engine()), id(cn.engine()))
+        sig = (V, h, w, cfg, lc, S, n_cam, pin_mode, id(un.engine()), id(cn.engine()),
+               tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items())))
         st = self._static
         if st is not None and st["sig"] == sig:
-            # same shapes as the resident state: refresh its buffers in place so a captured graph stays valid
-            st["latents"].copy_(lat_nhwc)
+            # same shapes as the resident state: refresh its input buffers in place (host -> device) and re-run the
+            # step-invariant encoders into the resident K/V / map buffers, so the captured step graph stays valid; from
+            # the second such call on that re-encode is itself one CUDA-graph replay
+            for k, v in inputs.items():
+                st["inputs"][k].copy_(v, non_blocking=True)
             if pin_mode is not None:
-                st["pin"]["mask"].copy_(pin_mask)
-                st["pin"]["cond"].copy_(pin_cond)
-                st["pin"]["noise0"].copy_(lat_nhwc)
-            st["map"].copy_(cond["map"])
-            for k, v in cond["kv"].items():
+                st["pin"]["noise0"].copy_(st["inputs"]["latents"])
+            st["guidance"], st["cond_scale"] = float(guidance_scale), float(controlnet_conditioning_scale)
+            if self.use_cuda_graph and st["inputs"]["latents"].is_cuda:
+                if self._cond_graph is None or self._cond_graph_state is not st:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._encode_conditions(st)
+                    self._cond_graph, self._cond_graph_state = g, st
+                self._cond_graph.replay()
+            else:
+                self._encode_conditions(st)
+            return st
+        dev_in = {k: v.to(dev) for k, v in inputs.items()}
+        st = dict(ue=un.engine(), ce=cn.engine(), V=V, h=h, w=w, S=S, n_cam=n_cam, cfg=cfg, sig=sig, inputs=dev_in,
+                  guidance=float(guidance_scale), cond_scale=float(controlnet_conditioning_scale), latents=dev_in["latents"],
+                  lc=lc, c_kv=None, u_kv=None, map=None,
+                  t_dev=torch.zeros(V, dtype=F32, device=dev),
+                  coef_dev=torch.zeros(len(self._coef_row()), dtype=F32, device=dev),
+                  hist=[torch.zeros_like(dev_in["latents"]) for _ in range(3)] if self.scheduler_name == "unipc" else [],
+                  pin=None if pin_mode is None else dict(
+                      mode=pin_mode, mask=dev_in["pin_mask"], cond=dev_in["pin_cond"], noise0=dev_in["latents"].clone(),
+                      coef_dev=torch.zeros(2, dtype=F32, device=dev), one=torch.tensor([0.0, 1.0], dtype=F32, device=dev)))
+        self._encode_conditions(st)
+        self._static, self._graph, self._cond_graph = st, None, None
+        return st
+
+    def _encode_conditions(self, st):
+        """Everything that depends on the conditioning but not on the latents or the timestep, from the resident input
+        buffers into the resident outputs: camera / box / text tokens (unet_addon_rawbox.py:743-793), their K/V projections
+        for the 7 + 16 transformers, the BEV-map embedding (map_embedder.py:66-76, once per scene)."""
+        ce, ue, x = st["ce"], st["ue"], st["inputs"]
+        boxes = None if "bboxes" not in x else dict(bboxes=x["bboxes"], classes=x["classes"], masks=x["masks"])
+        ctx = ce.context(x["camera"], boxes, x["text"])  # fp32 (V, Lc, 768)
+        assert ctx.shape[1] == st["lc"], (ctx.shape, st["lc"])
+        ctx_bf = ops.f32_to_bf16(ctx.reshape(-1, ctx.shape[-1]))
+        c_kv, u_kv = ce.context_kv(ctx_bf), ue.context_kv(ctx_bf)
+        memb = ce.map_embedding(x["image"]).repeat_interleave(st["n_cam"], dim=0).contiguous()  # 'b ... -> (b repeat) ...' (:842-843)
+        if st["c_kv"] is None:
+            st["c_kv"], st["u_kv"], st["map"] = c_kv, u_kv, memb
+        else:
+            st["map"].copy_(memb)
+            for k, v in c_kv.items():
                 st["c_kv"][k].copy_(v)
             for k, v in u_kv.items():
                 st["u_kv"][k].copy_(v)
-            st["guidance"], st["cond_scale"] = float(guidance_scale), float(controlnet_conditioning_scale)
-            return st
-        st = dict(ue=un.engine(), ce=cn.engine(), V=V, h=h, w=w, S=S, n_cam=n_cam, cfg=cfg, sig=sig,
-                  guidance=float(guidance_scale), cond_scale=float(controlnet_conditioning_scale), latents=lat_nhwc,
-                  c_kv={k: v.clone() for k, v in cond["kv"].items()}, u_kv={k: v.clone() for k, v in u_kv.items()},
-                  lc=lc, map=cond["map"].clone(),
-                  t_dev=torch.zeros(V, dtype=F32, device=dev),
-                  coef_dev=torch.zeros(len(self._coef_row()), dtype=F32, device=dev),
-                  hist=[torch.zeros_like(lat_nhwc) for _ in range(3)] if self.scheduler_name == "unipc" else [],
-                  pin=None if pin_mode is None else dict(
-                      mode=pin_mode, mask=pin_mask, cond=pin_cond, noise0=lat_nhwc.clone(),
-                      coef_dev=torch.zeros(2, dtype=F32, device=dev), one=torch.tensor([0.0, 1.0], dtype=F32, device=dev)))
-        self._static, self._graph = st, None
-        return st
 
     def _coef_row(self):
         return [0.0] * (2 if self.scheduler_name == "ddim" else UniPCSchedule.ROW)

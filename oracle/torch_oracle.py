@@ -183,7 +183,8 @@ def unet_forward(sd: SD, cfg: arch.UNetConfig, sample, timestep, encoder_hidden_
     emb = time_embedding(sd, t_emb)
     nb = cfg.neighboring_view_pair
     sample = _conv(sd, "conv_in", sample)
-    sample, skips = _encoder(sd, cfg, sample, emb, encoder_hidden_states, True, nb)
+    mv = cfg.multiview  # False = stock UNet2DConditionModel.forward (unet_2d_condition.py:600-792), same block sequencing
+    sample, skips = _encoder(sd, cfg, sample, emb, encoder_hidden_states, mv, nb)
     if down_block_additional_residuals is not None:
         skips = [s + r for s, r in zip(skips, down_block_additional_residuals)]
     if mid_block_additional_residual is not None:
@@ -196,7 +197,7 @@ def unet_forward(sd: SD, cfg: arch.UNetConfig, sample, timestep, encoder_hidden_
             sample = torch.cat([sample, res.pop()], dim=1)
             sample = resnet_block(sd, rs.prefix, sample, emb, g, eps)
             if tr is not None:
-                sample = transformer_2d(sd, tr.prefix, sample, encoder_hidden_states, tr.heads, True, nb, g)
+                sample = transformer_2d(sd, tr.prefix, sample, encoder_hidden_states, tr.heads, mv, nb, g)
         if blk.sampler is not None:
             sample = upsample(sd, blk.sampler.prefix, sample, skips[-1].shape[2:])
     sample = F.silu(F.group_norm(sample, g, sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], eps))

@@ -73,6 +73,37 @@ def test_module_forwards_through_emulated_operators_match_the_oracle(emulated, l
 
 
 @torch.no_grad()
+def test_configs0_one_view_text_only_stock_unet(emulated):
+    """BASELINE.json configs[0]: the stock SD-1.5 UNet2DConditionModel call (one view, text-only conditioning, single
+    denoise step, fp32 CPU plumbing).  (i) tiny config against the REFERENCE's own UNet2DConditionModel output
+    (tests/golden/plain_unet.pt <- oracle/make_golden_plain_unet.py) and the oracle; (ii) the real SD-1.5 config at
+    224x400 (28x50 latents), one view, against the oracle."""
+    from oracle.make_golden_plain_unet import tiny_plain_config
+    from tests.common import golden
+    g = golden("plain_unet.pt")
+    cfg = tiny_plain_config()
+    sd = arch.synthetic_state_dict(arch.unet_param_shapes(cfg), g["seed"])
+    assert not any(".attn4." in k or ".connector." in k for k in sd)  # stock BasicTransformerBlock
+    e32 = O.unet_forward(sd, cfg, g["sample"], torch.tensor(g["t"]), g["text"])
+    assert torch.allclose(e32, g["eps"], rtol=1e-3, atol=1e-4)  # oracle == reference, literal north-star tolerance
+    sdb = _bf16_exact(sd)
+    un = models.UNet2DConditionModelMultiview.stock_unet(**{k: v for k, v in asdict(cfg).items() if k != "neighboring_view_pair"})
+    un.load_state_dict(sdb)
+    out = un(g["sample"], g["t"], encoder_hidden_states=g["text"]).sample
+    assert out.shape == g["eps"].shape
+    assert rel_l2(out, O.unet_forward(sdb, cfg, g["sample"], torch.tensor(g["t"]), g["text"])) < 2e-5
+    # (ii) SD-1.5 size, 1 view, 77 text tokens
+    big = arch.UNetConfig(neighboring_view_pair={})
+    sdb = _bf16_exact(arch.synthetic_state_dict(arch.unet_param_shapes(big), 19))
+    un = models.UNet2DConditionModelMultiview.stock_unet()
+    un.load_state_dict(sdb)
+    gen = torch.Generator().manual_seed(6)
+    x, text = torch.randn(1, 4, 28, 50, generator=gen), torch.randn(1, 77, 768, generator=gen)
+    out = un(x, torch.tensor(981), encoder_hidden_states=text).sample
+    assert rel_l2(out, O.unet_forward(sdb, big, x, torch.tensor(981), text)) < 2e-5
+
+
+@torch.no_grad()
 def test_layernorm_fold_rounding_is_bf16_weight_noise(monkeypatch):
     """With the device's storage (W * gamma rounded to bf16) the folded path stays within bf16 weight-rounding noise of the
     fp32 oracle: the same size as the folded connector's rounding, far below the bf16 activation noise (8e-3, below)."""

@@ -170,9 +170,12 @@ def test_row_stats_and_folded_layernorm(cuda_lib, variant, m, c, n):
     r0 = _bf(torch.randn(m, c, device="cuda", generator=g))
     x, st = ops.linear(x0, w0, bias=b0, residual=r0, kernel_variant=variant, emit_stats=True)
     torch.cuda.synchronize()
+    # the statistics are accumulated from the fp32 values BEFORE their rounding to bf16 (zero-mean rounding noise of
+    # 2^-9 relative per element: far below what the consumer's normalisation can resolve)
     s = st.data.sum(1)
-    assert torch.allclose(s[:, 0], x.float().sum(-1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(s[:, 1], (x.float() ** 2).sum(-1), rtol=1e-4, atol=1e-2)
+    xf = x.float()
+    assert (s[:, 0] - xf.sum(-1)).abs().max().item() < 4e-3 * xf.abs().sum(-1).max().item() / math.sqrt(c) + 0.05
+    assert torch.allclose(s[:, 1], (xf ** 2).sum(-1), rtol=2e-3, atol=1e-2)
     gamma = torch.randn(c, device="cuda", generator=g) * 0.3 + 1.0
     beta = torch.randn(c, device="cuda", generator=g) * 0.2
     w = torch.randn(n, c, device="cuda", generator=g) / math.sqrt(c)

@@ -187,6 +187,38 @@ def test_sd15_three_step_cfg_loop_vs_fp32_oracle(cuda_lib, workload):
     assert (out[:, 0] - out[:, 1]).abs().max() > 1e-3
 
 
+@torch.no_grad()
+def test_configs0_stock_unet_one_view_text_only(cuda_lib):
+    """BASELINE.json configs[0] on the CUDA path: the stock UNet2DConditionModel call (one view, text-only) against the
+    reference's own output (tests/golden/plain_unet.pt) and, at SD-1.5 size / 224x400, against the fp32 oracle."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from oracle.make_golden_plain_unet import tiny_plain_config
+    g = golden("plain_unet.pt")
+    cfg = tiny_plain_config()
+    sd = arch.synthetic_state_dict(arch.unet_param_shapes(cfg), g["seed"])
+    kw = {k: v for k, v in asdict(cfg).items() if k != "neighboring_view_pair"}
+    un = UNet2DConditionModelMultiview.stock_unet(**kw)
+    un.load_state_dict(sd)
+    un = un.to(DEV)
+    out = un(g["sample"].to(DEV), g["t"], encoder_hidden_states=g["text"].to(DEV)).sample
+    sb = {k: v.to(DEV, torch.bfloat16) for k, v in sd.items()}
+    yard = O.unet_forward(sb, cfg, g["sample"].to(DEV, torch.bfloat16), torch.tensor(g["t"], device=DEV), g["text"].to(DEV, torch.bfloat16))
+    _check("configs[0] tiny stock UNet vs reference fixture", out, g["eps"], yard)
+    big = arch.UNetConfig(neighboring_view_pair={})
+    sd = arch.synthetic_state_dict(arch.unet_param_shapes(big), 19)
+    un = UNet2DConditionModelMultiview.stock_unet()
+    un.load_state_dict(sd)
+    un = un.to(DEV, torch.bfloat16)
+    gen = torch.Generator().manual_seed(6)
+    x, text = torch.randn(1, 4, 28, 50, generator=gen).to(DEV), torch.randn(1, 77, 768, generator=gen).to(DEV)
+    t = torch.tensor(981, device=DEV)
+    out = un(x.bfloat16(), t, encoder_hidden_states=text.bfloat16()).sample
+    truth = O.unet_forward({k: v.to(DEV) for k, v in sd.items()}, big, x, t, text)
+    yard = O.unet_forward({k: v.to(DEV, torch.bfloat16) for k, v in sd.items()}, big, x.bfloat16(), t, text.bfloat16())
+    _check("configs[0] SD-1.5 stock UNet 1 view 224x400", out, truth, yard)
+
+
 def _tiny_case(scenes, n_box, seed, masks_off=False):
     from magicdrive_b200.synthetic import synthetic_inputs
     inp = synthetic_inputs(scenes, 6, 10, 13, n_box=n_box, map_hw=52, seed=seed)

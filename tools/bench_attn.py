@@ -15,7 +15,38 @@ SHAPES = [  # (b, heads, lq, lk, d, sets)
 ]
 
 
+def trace_one(b, h, lq, lk, d, sets):
+    """Phase stamps of the first CTA of attention_tc2 (mdb_attention_debug_trace): cycles per KV iteration."""
+    from magicdrive_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(0)
+    c = h * d
+    q = torch.randn(b * lq, c, device="cuda", generator=g).bfloat16()
+    k = torch.randn(b * lk, c, device="cuda", generator=g).bfloat16()
+    v = torch.randn(b * lk, c, device="cuda", generator=g).bfloat16()
+    run = lambda: ops.attention(q, k, v, b=b, heads=h, lq=lq, lk=lk, d=d, ldq=c, ldk=c, ldv=c, scale=d ** -0.5)
+    for _ in range(3):
+        run()
+    tr = torch.zeros(3 * 16 * 8, dtype=torch.int64, device="cuda")
+    _lib.lib().mdb_attention_debug_trace(tr.data_ptr())
+    run()
+    torch.cuda.synchronize()
+    _lib.lib().mdb_attention_debug_trace(None)
+    t = tr.view(3, 16, 8).cpu()
+    t0 = int(t[0, 0, 0])
+    print(f"B={b} H={h} Lq={lq} Lk={lk} D={d}: first CTA, cycles since the MMA warp's first wait")
+    names = [["wait_p", "p_full", "pv_issued", "qk_issued"], ["wait_s", "s_full", "ldtm", "max", "exp", "sttm", "arrived"]]
+    for it in range(min(16, (lk + 127) // 128 * sets)):
+        mm = " ".join(f"{n}={int(t[0, it, i]) - t0}" for i, n in enumerate(names[0]))
+        s0 = " ".join(f"{n}={int(t[1, it, i]) - t0}" for i, n in enumerate(names[1]))
+        s1 = " ".join(f"{n}={int(t[2, it, i]) - t0}" for i, n in enumerate(names[1]))
+        print(f"  it {it:2d} MMA: {mm}\n        sm0: {s0}\n        sm1: {s1}")
+
+
 def main():
+    if "--trace" in sys.argv:
+        trace_one(12, 8, 1400, 1400, 40, 1)
+        trace_one(12, 8, 350, 350, 80, 1)
+        return
     kernels = sys.argv[1:] or ["tc2", "tc2d", "tc"]
     g = torch.Generator(device="cuda").manual_seed(0)
     nbr = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}

@@ -106,6 +106,8 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
     for _ in range(args.reps):
         if not args.warm:
             flush.zero_()
+        else:
+            torch.cuda._sleep(400000)  # ~0.2 ms spin: the launch below is enqueued before the GPU gets to it (no host-bound gap)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.gemm_conv(x, wt, **kw)

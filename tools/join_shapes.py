@@ -16,7 +16,7 @@ for row in r:
     v = v / 1e3 if row[ui] == "ns" else (v * 1e3 if row[ui] == "ms" else v)
     launches.append((re.sub(r"\(.*", "", row[ki]), v))
 shapes = [l.rstrip("\n").split("\t") for l in open(shape_log)]
-tc = [(n, t) for n, t in launches if "gemm_tc" in n or "attention" in n or "splitk_finalize" in n]
+tc = [(n, t) for n, t in launches if "gemm_tc" in n or "gemm_pair" in n or "attention" in n or "splitk_finalize" in n]
 agg = collections.OrderedDict()
 i = 0
 for kind, fl, info in shapes:

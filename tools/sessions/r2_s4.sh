@@ -1,0 +1,29 @@
+#!/bin/bash
+# round-2 GPU session 4: packed-math epilogue (G = 2 / 3 / 4 warp groups) correctness + timing, attention phase trace
+mkdir -p gpurun_out/s4
+O=gpurun_out/s4
+V=magicdrive_b200/lib/variants
+timeout 300 python -m pytest tests/test_gemm_pair_gpu.py -x -q -m gpu 2>&1 | tail -6 > $O/pair_tests_g4.log
+for g in epi2 epi3; do
+  MDB_LIB_PATH=$V/lib$g.so timeout 300 python -m pytest tests/test_gemm_pair_gpu.py -x -q -m gpu 2>&1 | tail -4 > $O/pair_tests_$g.log
+done
+MDB_GEMM_VARIANT=3 timeout 200 python tools/bench_gemm.py --warm > $O/warm_pair_g4.log 2>&1
+for g in epi2 epi3; do
+  MDB_LIB_PATH=$V/lib$g.so MDB_GEMM_VARIANT=3 timeout 200 python tools/bench_gemm.py --warm > $O/warm_pair_$g.log 2>&1
+done
+MDB_GEMM_VARIANT=2 timeout 200 python tools/bench_gemm.py --warm > $O/warm_tc2.log 2>&1
+MDB_GEMM_VARIANT=4 timeout 200 python tools/bench_gemm.py --warm > $O/warm_single_g4.log 2>&1
+MDB_GEMM_VARIANT=3 timeout 120 python tools/bench_gemm.py --trace --warm --only tok16800_320x > $O/trace_pair_warm.log 2>&1
+timeout 120 python tools/bench_attn.py --trace > $O/attn_trace.log 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > $O/pytest_gpu.log
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference > $O/bench_full.json 2> $O/bench_full.err
+for g in epi2 epi3; do
+  MDB_LIB_PATH=$V/lib$g.so timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference > $O/bench_full_$g.json 2> $O/bench_full_$g.err
+done
+timeout 600 ncu --profile-from-start off --cache-control none --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_step.csv python tools/profile_step.py --workload full --shape-log $O/shapes.txt > $O/ncu_step.log 2>&1
+tail -n 8 $O/*.log; for f in $O/bench_*.json; do echo $f; python -c "
+import json,sys
+try:
+    d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['roofline']['frac'], 'gemm ms', d['roofline']['kernel_ms_per_step'], d['gpu_launches_per_step'])
+except Exception as e: print('ERR', e)
+"; done
