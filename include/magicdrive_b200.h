@@ -186,6 +186,22 @@ int mdb_cfg_unipc_step(const float* eps, int eps_ld, int c, int cfg, float guida
 int mdb_pin_views(float* dst, int dst_ld, const float* a, const float* b, int c, const float* coef, const int* view_mask,
                   long long rows_per_view, int n_views, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input preparation (the step before the path; magicdrive/dataset/utils.py:120-352, demo/helper.py:386-466).
+ * mdb_prepare_boxes: for every (scene, camera view) keep the boxes that have at least one corner in front of the camera
+ * (z > 0 in the frame img_aug @ lidar2camera; the TEST uses the box shifted down by dz/2 exactly like the reference's
+ * box_center_shift), compacted in their original order, as 8 corners (mmdet3d order) of the ORIGINAL box.
+ *   boxes: fp32 [sum n_s, box_dim] rows (x, y, z, dx, dy, dz, yaw, ...), bottom-centred; labels: int64 [sum n_s];
+ *   box_offsets: int32 [n_scenes + 1]; lidar2camera, img_aug (may be NULL): fp32 [n_scenes, n_views, 4, 4];
+ *   out_boxes fp32 [n_scenes, n_views, capacity, 8, 3] (0-padded), out_classes int64 [.., capacity] (-1 padded),
+ *   out_masks uint8 [.., capacity], out_counts int32 [n_scenes, n_views] (visible boxes, may exceed capacity: overflow is dropped).
+ * mdb_camera_param: out fp32 [n, 3, 7] = [K[:3,:3] | (lidar2camera^-1)[:3]] for n = scenes * views rigid transforms
+ * (dataset/utils.py:294-297). */
+int mdb_prepare_boxes(const float* boxes, int box_dim, const long long* labels, const int* box_offsets, int n_scenes,
+                      const float* lidar2camera, const float* img_aug, int n_views, int capacity, float* out_boxes,
+                      long long* out_classes, unsigned char* out_masks, int* out_counts, void* stream);
+int mdb_camera_param(const float* intrinsics, const float* lidar2camera, int n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,3 +27,7 @@ try:
     d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['roofline']['frac'], 'gemm ms', d['roofline']['kernel_ms_per_step'], d['gpu_launches_per_step'])
 except Exception as e: print('ERR', e)
 "; done
+# instruction-level profile of the pair kernel on the epilogue-bound token GEMMs (default build)
+MDB_GEMM_VARIANT=3 timeout 600 ncu --profile-from-start off --set full --import-source on --clock-control none --cache-control none \
+  -k regex:gemm_pair -o $O/prof_pair python tools/bench_gemm.py --profile --warm --only tok16800 > $O/ncu_pair.log 2>&1
+tail -3 $O/ncu_pair.log
