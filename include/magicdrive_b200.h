@@ -67,9 +67,8 @@ typedef struct {
   size_t workspace_bytes;
   int force_block_n;    /* 0 = auto; test hook */
   int force_splits;     /* 0 = auto; test hook */
-  int kernel_variant;   /* 0 = auto (CTA-pair kernel where it applies, else the single-CTA split-K kernel); 1 = first
-                         * one-tile-per-CTA kernel; 2 = single-CTA persistent kernel; 3 = CTA-pair kernel; 4 = the pair
-                         * kernel's code on single CTAs; test / A-B hook */
+  int kernel_variant;   /* 0 = auto (CTA-pair kernel where it applies, else the single-CTA split-K kernel); 2 = single-CTA
+                         * persistent kernel; 3 = CTA-pair kernel; 4 = the pair kernel's code on single CTAs; test / A-B hook */
   int debug_flags;      /* ablation hook (0 in production): 1 skip stores, 2 skip epilogue loads, 4 skip TMEM loads */
   void* trace;          /* debug: device int64[8*16] receiving per-CTA clock64 stamps of the persistent kernel, or NULL */
   /* LayerNorm folded into the GEMM (attention.py:85,104,120; blocks.py:67-71): A is the RAW tensor x, W was
@@ -126,6 +125,14 @@ int mdb_softmax_rows(const float* s, int lds, long long rows, int cols, void* ou
  * (attention_processor.py:1165-1171, 1252). */
 int mdb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int b,
                   int b_kv, int heads, int lq, int lk, int d, const int* kv_index, int n_sets, float scale, void* stream);
+
+/* The same with the K/V batches spread over n_src (1..3) buffers: k[i] / v[i] are [b_kv[i], Lk, heads*d] with row strides
+ * ldk[i] / ldv[i]; kv_index entries are (source << 24) | batch index inside that source.  This is how the view-sharded mode
+ * consumes its ring neighbours' K/V without gathering them: source 1 / 2 are the neighbour GPUs' K/V buffers, mapped through
+ * NVLink peer memory (the TMA loads go over NVLink tile by tile, overlapping the local QK^T / PV work). */
+int mdb_attention_multi(const void* q, int ldq, int n_src, const void* const* k, const int* ldk, const void* const* v,
+                        const int* ldv, const int* b_kv, void* out, int ldo, int b, int heads, int lq, int lk, int d,
+                        const int* kv_index, int n_sets, float scale, void* stream);
 
 /* Debug hook (NULL in production): a device int64[3 * 16 * 8] buffer that receives clock64 stamps of the first CTA of
  * every following fused-attention launch (MMA warp and two softmax warps, 16 KV iterations, 8 points each);

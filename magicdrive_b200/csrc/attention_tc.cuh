@@ -18,12 +18,20 @@ namespace mdb {
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 128;
 
+// K/V of a call may live in up to three buffers (this GPU's and, in view-sharded runs, the two ring-neighbour GPUs' buffers
+// mapped through NVLink peer memory): kv_index entries are (source << 24) | batch index inside that source.
+constexpr int ATT_MAX_SRC = 3;
+struct AttnKvMaps {
+  CUtensorMap k[ATT_MAX_SRC], v[ATT_MAX_SRC];
+};
+
 struct AttnTcParams {
   __nv_bfloat16* out;
   int ldo;
   int lq, lk;
   const int* kv_index;
   int n_sets;
+  int n_src;
   float scale_log2;
   long long* trace;  // debug (mdb_attention_debug_trace): clock64 stamps of CTA (0,0,0): [3 warps][16 iterations][8 points]
 };
@@ -88,8 +96,8 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr_b
 
 template <int D>
 __global__ void __launch_bounds__(AttnTcCfg<D>::kThreads, (D <= 64) ? 2 : 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnKvMaps kvm,
+                    const AttnTcParams p) {
   using Cfg = AttnTcCfg<D>;
   constexpr int KD = Cfg::KD, D16 = Cfg::D16, STAGES = Cfg::STAGES, TILE = Cfg::TILE;
   extern __shared__ uint8_t smem_raw[];
@@ -115,8 +123,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
-    prefetch_tmap(&tmK);
-    prefetch_tmap(&tmV);
+    for (int i = 0; i < p.n_src; ++i) {
+      prefetch_tmap(&kvm.k[i]);
+      prefetch_tmap(&kvm.v[i]);
+    }
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -149,14 +159,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int set = 0; set < p.n_sets; ++set) {
-        const int kvb = p.kv_index ? p.kv_index[b * p.n_sets + set] : b;
+        const int kve = p.kv_index ? p.kv_index[b * p.n_sets + set] : b;
+        const int kvb = kve & 0xffffff;
+        const CUtensorMap* km = &kvm.k[kve >> 24];
+        const CUtensorMap* vm = &kvm.v[kve >> 24];
         for (int j = 0; j < ntiles; ++j) {
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&kv_full[stage], 2 * KD * TILE);
 #pragma unroll
           for (int c = 0; c < KD; ++c) {
-            tma_load_4d(&tmK, &kv_full[stage], smK + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
-            tma_load_4d(&tmV, &kv_full[stage], smV + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
+            tma_load_4d(km, &kv_full[stage], smK + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
+            tma_load_4d(vm, &kv_full[stage], smV + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
           }
           if (++stage == STAGES) {
             stage = 0;

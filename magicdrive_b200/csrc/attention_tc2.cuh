@@ -45,8 +45,8 @@ constexpr float ATT_LAZY_LOG2 = 8.0f;  // raise the reference maximum only when 
 
 template <int D, bool DOUBLE_S>
 __global__ void __launch_bounds__(AttnTc2Cfg<D, DOUBLE_S>::kThreads, AttnTc2Cfg<D, DOUBLE_S>::kMinCtas)
-attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnKvMaps kvm,
+                     const AttnTcParams p) {
   using Cfg = AttnTc2Cfg<D, DOUBLE_S>;
   constexpr int KD = Cfg::KD, D16 = Cfg::D16, STAGES = Cfg::STAGES, TILE = Cfg::TILE, HW = Cfg::HW, NBUF = Cfg::NBUF;
   extern __shared__ uint8_t smem_raw[];
@@ -79,8 +79,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
-    prefetch_tmap(&tmK);
-    prefetch_tmap(&tmV);
+    for (int i = 0; i < p.n_src; ++i) {
+      prefetch_tmap(&kvm.k[i]);
+      prefetch_tmap(&kvm.v[i]);
+    }
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -116,14 +118,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int set = 0; set < p.n_sets; ++set) {
-        const int kvb = p.kv_index ? p.kv_index[b * p.n_sets + set] : b;
+        const int kve = p.kv_index ? p.kv_index[b * p.n_sets + set] : b;
+        const int kvb = kve & 0xffffff;
+        const CUtensorMap* km = &kvm.k[kve >> 24];
+        const CUtensorMap* vm = &kvm.v[kve >> 24];
         for (int j = 0; j < ntiles; ++j) {
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&kv_full[stage], 2 * KD * TILE);
 #pragma unroll
           for (int c = 0; c < KD; ++c) {
-            tma_load_4d(&tmK, &kv_full[stage], smK + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
-            tma_load_4d(&tmV, &kv_full[stage], smV + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
+            tma_load_4d(km, &kv_full[stage], smK + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
+            tma_load_4d(vm, &kv_full[stage], smV + (stage * KD + c) * TILE, c * 64, head, j * ATT_BN, kvb);
           }
           if (++stage == STAGES) {
             stage = 0;

@@ -9,7 +9,6 @@
 #include "../../include/magicdrive_b200.h"
 #define MDB_NEED_TENSORMAP
 #include "common_host.h"
-#include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_pair.cuh"
 
@@ -150,23 +149,6 @@ void make_plan(const mdb_gemm_desc* d, Plan* pl) {
   }
   pl->kb_per_split = (pl->kb_total + splits - 1) / splits;
   pl->splits = (pl->kb_total + pl->kb_per_split - 1) / pl->kb_per_split;  // no empty split
-}
-
-template <int BN>
-int launch(const mdb_gemm_desc* d, const Plan& pl, const CUtensorMap& tA0, const CUtensorMap& tA1,
-           const CUtensorMap& tB, const GemmParams& gp, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<BN>::kSmemBytes);
-    if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  dim3 grid(pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles, pl.splits);
-  gemm_tc_kernel<BN><<<grid, 256, GemmCfg<BN>::kSmemBytes, st>>>(tA0, tA1, tB, gp);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "gemm_tc_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
-  return MDB_OK;
 }
 
 template <int BN>
@@ -421,20 +403,11 @@ extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
   gp.trace = static_cast<long long*>(d->trace);
   gp.debug_flags = d->debug_flags;
 
-  if (d->kernel_variant != 1) {
-    switch (pl.block_n) {
-      case 256: rc = launch2<256>(pl, tA0, tA1, tB, gp, st); break;
-      case 160: rc = launch2<160>(pl, tA0, tA1, tB, gp, st); break;
-      case 128: rc = launch2<128>(pl, tA0, tA1, tB, gp, st); break;
-      case 64: rc = launch2<64>(pl, tA0, tA1, tB, gp, st); break;
-      default: return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: unsupported block_n %d", pl.block_n);
-    }
-  } else
   switch (pl.block_n) {
-    case 256: rc = launch<256>(d, pl, tA0, tA1, tB, gp, st); break;
-    case 160: rc = launch<160>(d, pl, tA0, tA1, tB, gp, st); break;
-    case 128: rc = launch<128>(d, pl, tA0, tA1, tB, gp, st); break;
-    case 64: rc = launch<64>(d, pl, tA0, tA1, tB, gp, st); break;
+    case 256: rc = launch2<256>(pl, tA0, tA1, tB, gp, st); break;
+    case 160: rc = launch2<160>(pl, tA0, tA1, tB, gp, st); break;
+    case 128: rc = launch2<128>(pl, tA0, tA1, tB, gp, st); break;
+    case 64: rc = launch2<64>(pl, tA0, tA1, tB, gp, st); break;
     default: return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: unsupported block_n %d", pl.block_n);
   }
   if (rc != MDB_OK) return rc;

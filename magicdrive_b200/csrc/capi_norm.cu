@@ -1,6 +1,5 @@
 // GroupNorm(+SiLU) over NHWC (optionally over a two-source channel concat) and LayerNorm.  HBM-bound kernels:
 // 16-byte vector loads along the contiguous channel axis, fp32 statistics, warp-shuffle / smem reductions.
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -273,132 +272,6 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
-// ---- GroupNorm, pixel-major variant on a thread-block cluster (opt-in: MDB_GN_CLUSTER=1, not yet measured).
-// One cluster per image, each CTA owns a contiguous run of pixels with ALL channels, so every global access is a
-// 16-byte vector along the contiguous channel axis (the (image, group) CTAs of gn_fused_kernel touch 2*cpg bytes per
-// pixel).  The CTA keeps its pixels in shared memory, computes per-group (mean, M2) locally in two passes over that
-// slab, publishes them, and after ONE cluster barrier every CTA combines the partitions' statistics through
-// distributed shared memory (Chan's parallel variance: exact, no E[x^2] - mean^2 cancellation), then normalises its
-// pixels and stores.  thread = (pixel lane r, channel vector cv) with blockDim = vpp * R, so a thread's 8 channels,
-// their groups, gamma and beta are fixed for the whole kernel.
-constexpr int GN_MAX_GROUPS = 64;
-__global__ void gn_cluster_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0, const __nv_bfloat16* __restrict__ x1,
-                                  int c1, int ld1, int hw, int groups, float eps, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ out, int ldo,
-                                  int vpp, int R, int pix_per_cta) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ uint4 gslab[];              // [pix_per_cta][vpp]
-  __shared__ float g_sum[GN_MAX_GROUPS];        // scratch accumulators
-  __shared__ float g_part[2 * GN_MAX_GROUPS];   // published: local mean, local M2 (read by the other CTAs)
-  __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
-  const unsigned csize = cluster.num_blocks(), rank = cluster.block_rank();
-  const int img = blockIdx.x / csize;
-  const int ctot = c0 + c1, cpg = ctot / groups;
-  const int p_begin = min(hw, static_cast<int>(rank) * pix_per_cta), p_end = min(hw, p_begin + pix_per_cta);
-  const int npix = p_end - p_begin;
-  const int cv = threadIdx.x % vpp, r0 = threadIdx.x / vpp;
-  const int ch = cv * 8;
-  const long long pix0 = static_cast<long long>(img) * hw + p_begin;
-  const __nv_bfloat16* src = (ch < c0) ? x0 + pix0 * ld0 + ch : x1 + pix0 * ld1 + (ch - c0);
-  const int lds = (ch < c0) ? ld0 : ld1;
-  int grp[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) grp[e] = (ch + e) / cpg;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) g_sum[g] = 0.f;
-  // ---- load the pixel run once (coalesced 16-byte vectors), keep it in shared memory
-  for (int p = r0; p < npix; p += R) gslab[p * vpp + cv] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * lds));
-  __syncthreads();
-  // ---- local mean per group
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int p = r0; p < npix; p += R) {
-    float f[8];
-    unpack8(gslab[p * vpp + cv], f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += f[e];
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) atomicAdd(&g_sum[grp[e]], acc[e]);
-  __syncthreads();
-  const float cnt_local = static_cast<float>(npix) * static_cast<float>(cpg);
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    g_part[g] = npix > 0 ? g_sum[g] / cnt_local : 0.f;
-    g_sum[g] = 0.f;
-  }
-  __syncthreads();
-  // ---- local M2 per group around the local mean
-  float lm[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) lm[e] = g_part[grp[e]], acc[e] = 0.f;
-  for (int p = r0; p < npix; p += R) {
-    float f[8];
-    unpack8(gslab[p * vpp + cv], f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = f[e] - lm[e];
-      acc[e] += d * d;
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) atomicAdd(&g_sum[grp[e]], acc[e]);
-  __syncthreads();
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) g_part[GN_MAX_GROUPS + g] = g_sum[g];
-  cluster.sync();  // every CTA's (mean, M2) is published
-  // ---- combine the partitions (Chan et al.): mean = sum n_i m_i / N, M2 = sum M2_i + sum n_i (m_i - mean)^2
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float wsum = 0.f;
-    for (unsigned r = 0; r < csize; ++r) {
-      const int nb = min(hw, static_cast<int>(r) * pix_per_cta), ne = min(hw, nb + pix_per_cta);
-      wsum += static_cast<float>(ne - nb) * cluster.map_shared_rank(g_part, r)[g];
-    }
-    const float mean = wsum / static_cast<float>(hw);
-    float m2 = 0.f;
-    for (unsigned r = 0; r < csize; ++r) {
-      const int nb = min(hw, static_cast<int>(r) * pix_per_cta), ne = min(hw, nb + pix_per_cta);
-      const float* rp = cluster.map_shared_rank(g_part, r);
-      const float d = rp[g] - mean;
-      m2 += rp[GN_MAX_GROUPS + g] + static_cast<float>(ne - nb) * static_cast<float>(cpg) * d * d;
-    }
-    g_mean[g] = mean;
-    g_rstd[g] = rsqrtf(m2 / (static_cast<float>(hw) * static_cast<float>(cpg)) + eps);
-  }
-  __syncthreads();
-  // ---- normalise + affine (+SiLU), coalesced 16-byte stores
-  float ga[8], be[8], mu[8], rs[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    ga[e] = __ldg(gamma + ch + e), be[e] = __ldg(beta + ch + e);
-    mu[e] = g_mean[grp[e]], rs[e] = g_rstd[grp[e]];
-  }
-  __nv_bfloat16* dst = out + pix0 * ldo + ch;
-  for (int p = r0; p < npix; p += R) {
-    float f[8];
-    unpack8(gslab[p * vpp + cv], f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float y = (f[e] - mu[e]) * rs[e] * ga[e] + be[e];
-      if (silu) y = y / (1.0f + __expf(-y));
-      f[e] = y;
-    }
-    *reinterpret_cast<uint4*>(dst + static_cast<long long>(p) * ldo) = pack8(f);
-  }
-  cluster.sync();  // nobody leaves while a neighbour may still read its published statistics
-}
-
-// cluster size (1, 2, 4 or 8 CTAs per image) such that one CTA's pixel run fits in shared memory; 0 = does not fit
-inline int gn_cluster_size(int hw, int ctot, size_t* smem_bytes, int* pix_per_cta) {
-  for (int cs = 1; cs <= 8; cs *= 2) {
-    const int ppc = (hw + cs - 1) / cs;
-    const size_t bytes = static_cast<size_t>(ppc) * ctot * 2;
-    if (bytes <= 160 * 1024) {
-      // prefer at least ~128 CTAs overall is the caller's business; here: smallest cluster whose slab fits
-      *smem_bytes = bytes, *pix_per_cta = ppc;
-      return cs;
-    }
-  }
-  return 0;
-}
-
 }  // namespace
 
 extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int n_img, int hw,
@@ -412,40 +285,6 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
                      groups);
   if (c1 > 0 && !x1) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: c1>0 but x1 null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* use_cluster = getenv("MDB_GN_CLUSTER");
-  if (use_cluster && use_cluster[0] == '1' && groups <= GN_MAX_GROUPS && ctot / 8 <= 1024) {
-    size_t slab = 0;
-    int ppc = 0;
-    int cs = gn_cluster_size(hw, ctot, &slab, &ppc);
-    // spread small images over more CTAs (the grid is cs * n_img): keep halving the run while the machine is under-filled
-    while (cs && cs < 8 && cs * n_img < 148 && ppc > 32) {
-      cs *= 2;
-      ppc = (hw + cs - 1) / cs;
-      slab = static_cast<size_t>(ppc) * ctot * 2;
-    }
-    if (cs) {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr = true;
-      }
-      const int vpp = ctot / 8;
-      int R = 256 / vpp;
-      if (R < 1) R = 1;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(cs * n_img), cfg.blockDim = dim3(vpp * R), cfg.dynamicSmemBytes = slab, cfg.stream = st;
-      cudaLaunchAttribute la[1];
-      la[0].id = cudaLaunchAttributeClusterDimension;
-      la[0].val.clusterDim.x = cs, la[0].val.clusterDim.y = 1, la[0].val.clusterDim.z = 1;
-      cfg.attrs = la, cfg.numAttrs = 1;
-      cudaError_t le = cudaLaunchKernelEx(&cfg, gn_cluster_kernel, static_cast<const __nv_bfloat16*>(x0), c0, ld0,
-                                          static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps, gamma, beta, silu,
-                                          static_cast<__nv_bfloat16*>(out), ldo, vpp, R, ppc);
-      if (le != cudaSuccess) return set_error(MDB_ERR_CUDA, "gn_cluster_kernel launch: %s", cudaGetErrorString(le));
-      MDB_CHECK_LAUNCH("gn_cluster_kernel");
-      return MDB_OK;
-    }
-  }
   if (((ctot / groups) & 1) == 0 && (c0 & 1) == 0 && !getenv("MDB_GN_TWO_KERNEL")) {
     const int pp = ctot / groups / 2;
     const long long units = static_cast<long long>(hw) * pp;

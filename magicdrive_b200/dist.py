@@ -143,3 +143,75 @@ class ViewShard:
         bufs = [torch.empty_like(local) for _ in range(self.world)]
         dist.all_gather(bufs, local.contiguous(), group=self.group)
         return torch.cat(bufs, dim=1)
+
+
+class ShardPlan:
+    """How ONE scene's 12 guidance x view samples are spread over `world` ranks for low latency (BASELINE.json north_star,
+    SURVEY.md section 8e).  Two independent cuts:
+      * guidance halves (uncond | cond): no coupling inside the networks at all; the halves meet only in the guidance
+        combine of the scheduler step (pipeline_bev_controlnet.py:426-428), where each rank reads its partner's predicted
+        noise.  Used whenever classifier-free guidance is on and `world` is even.
+      * camera views: contiguous ranges of the ring FL, F, FR, BR, B, BL over the `groups` ranks of a half (uneven allowed,
+        e.g. 2+2+1+1 on 4 ranks).  The only coupling is the neighbour-view attention (blocks.py:113-121): a rank needs the K/V
+        of the view left of its first view and right of its last view, i.e. one view of each ring neighbour rank — read in
+        place through NVLink peer memory (no gather, no copy).
+    world 2 -> halves only (zero exchange inside the UNet); 4 -> halves x (3+3 views); 8 -> halves x (2+2+1+1 views);
+    without guidance or with an odd world the ranks only split the views."""
+
+    def __init__(self, rank: int, world: int, n_cam: int, cfg: bool, pairs: Sequence[Sequence[int]]):
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError(f"bad rank/world {rank}/{world}")
+        self.rank, self.world, self.n_cam, self.cfg = rank, world, n_cam, cfg
+        self.split_cfg = bool(cfg and world % 2 == 0)
+        self.groups = world // 2 if self.split_cfg else world        # ranks sharing the views of one half
+        if self.groups > n_cam:
+            raise ValueError(f"{world} ranks cannot share {n_cam} views" + (" (two guidance halves)" if self.split_cfg else ""))
+        self.half = rank // self.groups if self.split_cfg else 0      # 0 = unconditional, 1 = conditional
+        self.vg = rank % self.groups                                  # position on the view ring of this half
+        self.views = shard_range(n_cam, self.vg, self.groups)         # [begin, end) global view indices
+        self.n_local = self.views[1] - self.views[0]
+        self.pairs = [list(p) for p in pairs]
+        self.partner = (rank + self.groups) % world if self.split_cfg else rank   # same views, other guidance half
+        self.half_ranks = [self.half * self.groups + g for g in range(self.groups)]
+
+    def owner(self, view: int) -> Tuple[int, int]:
+        """(rank inside the half group, local view index on that rank) of a global view."""
+        for g in range(self.groups):
+            b, e = shard_range(self.n_cam, g, self.groups)
+            if b <= view < e:
+                return g, view - b
+        raise ValueError(view)
+
+    def local_views_of(self, g: int) -> int:
+        b, e = shard_range(self.n_cam, g, self.groups)
+        return e - b
+
+    def kv_sources(self, n_samples: int):
+        """For local batch (sample s, local view j) and each of its two ring neighbours: which K/V buffer holds it and at
+        which batch index.  Returns (sources, index): `sources` = ordered list of half-group ranks whose buffers are read
+        (this rank first), `index[(s * n_local + j) * 2 + side]` = (position in `sources`) << 24 | batch index there."""
+        sources = [self.vg]
+        idx = []
+        b0 = self.views[0]
+        for s in range(n_samples):
+            for j in range(self.n_local):
+                for side in range(2):
+                    g, lj = self.owner(self.pairs[b0 + j][side])
+                    if g not in sources:
+                        sources.append(g)
+                    idx.append((sources.index(g) << 24) | (s * self.local_views_of(g) + lj))
+        return sources, idx
+
+    def slice_views(self, inputs: dict) -> dict:
+        """Cut the view axis (dim 1) of camera_param / bboxes_3d_data / 5-D latents to this rank's views."""
+        b, e = self.views
+        n_cam = self.n_cam
+
+        def cut(k, v):
+            if isinstance(v, dict):
+                return {kk: cut(kk, x) for kk, x in v.items()}
+            if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == n_cam and (k != "latents" or v.dim() == 5) \
+                    and k not in ("prompt_embeds", "negative_prompt_embeds", "image", "bev_map"):
+                return v[:, b:e]
+            return v
+        return {k: cut(k, v) for k, v in inputs.items()}

@@ -28,7 +28,7 @@ def _conv_weight(wt):  # [co, ci, kh, kw] -> [co, kh*kw*ci] (tap-major, channel-
     return wt.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous()
 
 
-@pytest.mark.parametrize("variant", [0, 1])  # 0 = persistent double-buffered kernel, 1 = one tile per CTA
+@pytest.mark.parametrize("variant", [0, 2])  # 0 = planner's choice (CTA-pair kernel where it applies), 2 = single-CTA persistent kernel
 @pytest.mark.parametrize("bn", [0, 64, 128, 160, 256])
 @pytest.mark.parametrize("m,k,n", [(1000, 320, 320), (128, 64, 640), (336, 1280, 1280), (16800, 320, 960)])
 def test_gemm_plain(cuda_lib, bn, m, k, n, variant):
@@ -76,7 +76,7 @@ def test_gemm_strided_views(cuda_lib):
     (2, 28, 50, 320, 320, 2), (3, 14, 25, 640, 640, 2), (5, 7, 13, 1280, 1280, 2), (1, 53, 100, 320, 320, 1),
     (12, 28, 50, 320, 320, 1),
 ])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 2])
 def test_conv3x3(cuda_lib, n, h, w, ci, co, stride, variant):
     g = torch.Generator(device="cuda").manual_seed(4)
     x = _bf(torch.randn(n, ci, h, w, device="cuda", generator=g))
@@ -156,7 +156,7 @@ def test_layernorm(cuda_lib, c):
     assert _rel(out, ref) < 8e-3
 
 
-ATTN_KERNELS = ["tc2", "tc2d", "tc", "legacy"]  # tcgen05 v2 (2 CTAs/SM | double-buffered S; d = 160 falls to tc), tcgen05 v1, mma.sync
+ATTN_KERNELS = ["tc2", "tc2d", "tc"]  # tcgen05 v2 (2 CTAs/SM | double-buffered S; d = 160 falls to tc), tcgen05 v1
 
 
 def _pick_attention_kernel(monkeypatch, kernel):
