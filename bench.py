@@ -230,8 +230,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
     by_views = args.shard == "views" and world > 1
-    sharding = (f"views: the 6 cameras of one scene split over {world} GPUs, cross-view K/V exchanged in each of the 16 multiview blocks"
-                if by_views else "scene-per-GPU replicas, no data-path collective")
+    sharding = (f"one scene over {world} GPUs: guidance halves x camera views; neighbour K/V and the partner half's noise read in "
+                "place through NVLink peer memory (no NCCL on the data path)" if by_views else "scene-per-GPU replicas, no data-path collective")
     config = workload_config(args, sharding)
     metric = "6-view 224x400 denoising-steps/sec" if args.res == "224x400" else "6-view 424x800 denoising-steps/sec"
 
@@ -273,13 +273,13 @@ def main():
     cn = BEVControlNetModel(**asdict(ccfg)).reset_parameters_synthetic(12).to(dev, torch.bfloat16)
     shard = None
     if by_views:
-        from magicdrive_b200.dist import ViewShard
-        shard = ViewShard(rank, world, 6)
+        from magicdrive_b200.dist import ShardContext
+        shard = ShardContext(6, True, [ucfg.neighboring_view_pair[i] for i in range(6)], dev)
     pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph, overlap_controlnet=not args.no_overlap,
                                  view_shard=shard, scheduler=args.scheduler, cfg_streams=args.cfg_streams)
     inp, h, w = make_inputs(args, 0 if by_views else rank)
     job_scenes = args.scenes if by_views else n_gpus * args.scenes  # scenes the whole job advances per step
-    views_local = 6 // world if by_views else 6
+    views_local = shard.plan.n_local * (0.5 if shard.plan.split_cfg else 1.0) if by_views else 6  # view-samples share of this rank
     boxes = inp["bboxes_3d_data"]
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
     if boxes is not None:
@@ -338,7 +338,8 @@ def main():
     #      back to the host.  The conditioning is a per-call constant staged before the loop (exactly as the reference
     #      pipeline moves it once, pipeline_bev_controlnet.py:329,343); the cost of re-staging + re-encoding it on
     #      EVERY step is reported separately as e2e_full_reencode.
-    lat_host = torch.stack([host["latents"]] * views_local, 1).permute(0, 1, 3, 4, 2).contiguous().view(-1, 4).pin_memory()
+    n_loc = shard.plan.n_local if by_views else 6
+    lat_host = torch.stack([host["latents"]] * n_loc, 1).permute(0, 1, 3, 4, 2).contiguous().view(-1, 4).pin_memory()
     out_host = torch.empty_like(lat_host).pin_memory()
     h2d = lat_host.numel() * 4 + 4 * st["V"]
     d2h = out_host.numel() * 4

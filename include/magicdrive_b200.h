@@ -100,7 +100,7 @@ int mdb_conv_direct(const void* x, int x_is_f32, int n, int h, int w, int cin, c
 
 /* GroupNorm (+SiLU) over NHWC, optionally over the channel-concat of two sources; writes one normalised tensor.
  * Replaces nn.GroupNorm + SiLU (resnet.py:535,556,598,630; transformer_2d.py:145; unet_2d_condition.py:492).
- * stats_ws: fp32 [n_img * groups * 2] scratch. */
+ * stats_ws: fp32 [max(n_img, 160) * groups * 2] scratch (per-image or per-CTA-run group partials). */
 int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int n_img, int hw, int groups,
                   float eps, const float* gamma, const float* beta, int silu, void* out, int ldo, float* stats_ws,
                   void* stream);
@@ -208,6 +208,14 @@ int mdb_prepare_boxes(const float* boxes, int box_dim, const long long* labels, 
                       const float* lidar2camera, const float* img_aug, int n_views, int capacity, float* out_boxes,
                       long long* out_classes, unsigned char* out_masks, int* out_counts, void* stream);
 int mdb_camera_param(const float* intrinsics, const float* lidar2camera, int n, float* out, void* stream);
+
+/* Barrier between the `world` GPUs of a sharding group over NVLink peer memory, as one stream operation (graph-capturable).
+ * flag_ptrs_dev: device array of `world` pointers, entry i = GPU i's symmetric uint32[n_channels * world] flag array as mapped
+ * into THIS GPU's address space; epoch_dev: this GPU's uint32[n_channels] counter; timed_out_dev: int set to 1 if a peer did
+ * not arrive within timeout_cycles SM cycles (0 = wait for ever).  Everything the peers wrote before their call is visible to
+ * the kernels launched after this one (the view-sharded cross-view attention reads the neighbours' K/V right after it). */
+int mdb_peer_barrier(void* const* flag_ptrs_dev, int rank, int world, int channel, int n_channels, void* epoch_dev,
+                     long long timeout_cycles, int* timed_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

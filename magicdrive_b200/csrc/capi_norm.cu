@@ -1,5 +1,6 @@
 // GroupNorm(+SiLU) over NHWC (optionally over a two-source channel concat) and LayerNorm.  HBM-bound kernels:
 // 16-byte vector loads along the contiguous channel axis, fp32 statistics, warp-shuffle / smem reductions.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -272,6 +273,130 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
+
+// ---- GroupNorm, pixel-major on a cooperative grid (MDB_GN_GRID=1).  Every image is split into contiguous pixel runs, one per
+// CTA (all CTAs co-resident: cooperative launch, grid <= SM count).  A CTA pulls its run into shared memory ONCE with coalesced
+// 16-byte loads, computes per-group (count, mean, M2) of the run exactly (two passes over shared memory), publishes them,
+// and after ONE grid barrier combines the runs of its image (Chan's parallel variance: no E[x^2] - mean^2 cancellation),
+// normalises its run from shared memory (+ affine, + SiLU) and stores it with coalesced 16-byte stores.  One global read and
+// one global write per element, both fully coalesced; gn_fused_kernel reads 20..80-byte channel slices per pixel instead.
+// blockDim = vpp * R (vpp = 16-byte vectors per pixel), thread = (pixel lane r, channel vector cv): a thread's 8 channels,
+// their groups, gamma and beta are fixed for the whole kernel.
+__global__ void gn_grid_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0, const __nv_bfloat16* __restrict__ x1,
+                               int c1, int ld1, int hw, int groups, float eps, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ out, int ldo, int vpp, int R,
+                               int ctas_per_img, int pix_per_cta, float* __restrict__ part /* [grid][groups][2] */) {
+  namespace cg = cooperative_groups;
+  extern __shared__ uint4 gslab[];  // [pix_per_cta][vpp] then float red[R][ctot]
+  const int ctot = c0 + c1, cpg = ctot / groups;
+  float* red = reinterpret_cast<float*>(gslab + static_cast<size_t>(pix_per_cta) * vpp);  // [R][ctot]
+  __shared__ float g_a[128], g_b[128];  // per group: local mean / M2, later mean / rstd
+  const int img = blockIdx.x / ctas_per_img, run = blockIdx.x % ctas_per_img;
+  const int p_begin = min(hw, run * pix_per_cta), p_end = min(hw, p_begin + pix_per_cta);
+  const int npix = p_end - p_begin;
+  const int cv = threadIdx.x % vpp, r0 = threadIdx.x / vpp;
+  const int ch = cv * 8;
+  const long long pix0 = static_cast<long long>(img) * hw + p_begin;
+  const __nv_bfloat16* src = (ch < c0) ? x0 + pix0 * ld0 + ch : x1 + pix0 * ld1 + (ch - c0);
+  const int lds = (ch < c0) ? ld0 : ld1;
+  // ---- one coalesced read of the run, kept in shared memory; per-thread channel sums on the way
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = r0; p < npix; p += R) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * lds));
+    gslab[p * vpp + cv] = u;
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[r0 * ctot + ch + e] = acc[e];
+  __syncthreads();
+  const float cnt_local = static_cast<float>(npix) * static_cast<float>(cpg);
+  for (int c = threadIdx.x; c < ctot; c += blockDim.x) {  // fold the R pixel lanes: red[0][c] = channel sum of the run
+    float s = red[c];
+    for (int r = 1; r < R; ++r) s += red[r * ctot + c];
+    red[c] = s;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < cpg; ++c) s += red[g * cpg + c];
+    g_a[g] = npix > 0 ? s / cnt_local : 0.f;  // local mean
+  }
+  __syncthreads();
+  // ---- local M2 around the local mean (second pass over shared memory)
+  float lm[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) lm[e] = g_a[(ch + e) / cpg], acc[e] = 0.f;
+  for (int p = r0; p < npix; p += R) {
+    float f[8];
+    unpack8(gslab[p * vpp + cv], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = f[e] - lm[e];
+      acc[e] = fmaf(d, d, acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[r0 * ctot + ch + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < ctot; c += blockDim.x) {
+    float s = red[c];
+    for (int r = 1; r < R; ++r) s += red[r * ctot + c];
+    red[c] = s;
+  }
+  __syncthreads();
+  float* mine = part + static_cast<size_t>(blockIdx.x) * groups * 2;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < cpg; ++c) s += red[g * cpg + c];
+    mine[2 * g] = g_a[g];
+    mine[2 * g + 1] = s;
+  }
+  __threadfence();
+  cg::this_grid().sync();  // every run's (mean, M2) is published
+  // ---- combine the runs of this image (Chan et al.): mean = sum n_i m_i / N, M2 = sum M2_i + sum n_i (m_i - mean)^2
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const float* base = part + static_cast<size_t>(img) * ctas_per_img * groups * 2;
+    float wsum = 0.f;
+    for (int r = 0; r < ctas_per_img; ++r) {
+      const int nb = min(hw, r * pix_per_cta), ne = min(hw, nb + pix_per_cta);
+      wsum += static_cast<float>(ne - nb) * __ldcg(base + (r * groups + g) * 2);
+    }
+    const float mean = wsum / static_cast<float>(hw);
+    float m2 = 0.f;
+    for (int r = 0; r < ctas_per_img; ++r) {
+      const int nb = min(hw, r * pix_per_cta), ne = min(hw, nb + pix_per_cta);
+      const float d = __ldcg(base + (r * groups + g) * 2) - mean;
+      m2 += __ldcg(base + (r * groups + g) * 2 + 1) + static_cast<float>(ne - nb) * static_cast<float>(cpg) * d * d;
+    }
+    g_a[g] = mean;
+    g_b[g] = rsqrtf(m2 / (static_cast<float>(hw) * static_cast<float>(cpg)) + eps);
+  }
+  __syncthreads();
+  // ---- normalise + affine (+SiLU) from shared memory, coalesced 16-byte stores
+  float sa[8], sb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float rs = g_b[(ch + e) / cpg], mu = g_a[(ch + e) / cpg];
+    sa[e] = rs * __ldg(gamma + ch + e);
+    sb[e] = __ldg(beta + ch + e) - mu * sa[e];
+  }
+  __nv_bfloat16* dst = out + pix0 * ldo + ch;
+  for (int p = r0; p < npix; p += R) {
+    float f[8];
+    unpack8(gslab[p * vpp + cv], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = fmaf(f[e], sa[e], sb[e]);
+      if (silu) y = y / (1.0f + __expf(-y));
+      f[e] = y;
+    }
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(p) * ldo) = pack8(f);
+  }
+}
+
 }  // namespace
 
 extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int n_img, int hw,
@@ -285,6 +410,49 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
                      groups);
   if (c1 > 0 && !x1) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: c1>0 but x1 null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // cooperative pixel-major kernel (opt-in while it is being measured: MDB_GN_GRID=1)
+    static int use_grid = -1, sms = 0;
+    if (use_grid < 0) {
+      const char* e = getenv("MDB_GN_GRID");
+      use_grid = (e && e[0] == '1') ? 1 : 0;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int vpp = ctot / 8;
+    if (use_grid && groups <= 128 && n_img <= sms && vpp <= 512) {
+      int R = 512 / vpp;
+      if (R < 1) R = 1;
+      int cpi = sms / n_img;                     // CTAs per image
+      if (cpi > (hw + R - 1) / R) cpi = (hw + R - 1) / R;
+      if (cpi < 1) cpi = 1;
+      const int ppc = (hw + cpi - 1) / cpi;
+      cpi = (hw + ppc - 1) / ppc;                // no empty runs
+      const size_t smem = static_cast<size_t>(ppc) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
+      if (smem <= 200 * 1024) {
+        static bool attr = false;
+        if (!attr) {
+          cudaFuncSetAttribute(gn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          attr = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cpi * n_img), cfg.blockDim = dim3(vpp * R), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeCooperative;
+        la[0].val.cooperative = 1;
+        cfg.attrs = la, cfg.numAttrs = 1;
+        // the per-run partials live at the tail of the caller's scratch (n_img * groups * 2 floats are reserved for the
+        // two-kernel path; the grid kernel needs grid * groups * 2 <= sms * groups * 2: the caller sizes stats_ws for that)
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_grid_kernel, static_cast<const __nv_bfloat16*>(x0), c0, ld0,
+                                            static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps, gamma, beta, silu,
+                                            static_cast<__nv_bfloat16*>(out), ldo, vpp, R, cpi, ppc, stats_ws);
+        if (le != cudaSuccess) return set_error(MDB_ERR_CUDA, "gn_grid_kernel launch: %s", cudaGetErrorString(le));
+        MDB_CHECK_LAUNCH("gn_grid_kernel");
+        return MDB_OK;
+      }
+    }
+  }
   if (((ctot / groups) & 1) == 0 && (c0 & 1) == 0 && !getenv("MDB_GN_TWO_KERNEL")) {
     const int pp = ctot / groups / 2;
     const long long units = static_cast<long long>(hw) * pp;

@@ -6,11 +6,12 @@ and cfg-half (magicdrive/networks/blocks.py:113-121).  Scene-sharding therefore 
 gathered once.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only for that gather, the barrier
 and the max-over-ranks timing.
 
-`ViewShard` is the second mode (BASELINE.json north_star: "NCCL all-gather of cross-view KV"): the cameras of ONE
-scene are split across ranks, for latency rather than throughput.  Everything on the path is per view except the
-neighbour-view attention, so the only exchange is one all-gather of that block's K/V projections per multiview
-transformer (16 per step); queries, softmax and the output stay local and address the gathered K/V through the
-kernel's kv_index (include/magicdrive_b200.h: mdb_attention, b_kv > b)."""
+`ShardPlan` / `ShardContext` are the second mode (BASELINE.json north_star: the cross-view K/V exchange): ONE scene's
+guidance halves and camera views are spread over the ranks, for latency rather than throughput.  Everything on the path
+is per (half, view) except the neighbour-view attention and the guidance combine, so the only exchanges are the two ring
+neighbours' K/V per multiview transformer (16 per step) and the partner half's predicted noise per step — both read /
+written IN PLACE through NVLink peer memory (symmetric allocations + a device-side barrier kernel), with no NCCL collective
+and no copy on the data path (include/magicdrive_b200.h: mdb_attention_multi, mdb_peer_barrier)."""
 import gc
 import os
 import sys
@@ -89,62 +90,6 @@ def max_over_ranks(value: float, device) -> float:
     return t.item()
 
 
-class ViewShard:
-    """Contiguous split of the n_cam cameras of every scene over the ranks of `group` (n_cam % world == 0).
-
-    Local sample order on every rank is (cfg-half, scene, local view), i.e. the unsharded order with the view axis cut;
-    `all_gather_rows` stacks the ranks' K/V row blocks in rank order, so the K/V batch of (sample s, global view g) sits
-    at  (g // n_local) * n_samples * n_local + s * n_local + g % n_local  — what `kv_index` returns for the two ring
-    neighbours of each local view (neighboring_view_pair, configs/dataset/Nuscenes.yaml:27-33)."""
-
-    def __init__(self, rank: int, world: int, n_cam: int, group: Optional["dist.ProcessGroup"] = None):
-        if n_cam % world:
-            raise ValueError(f"view sharding needs n_cam ({n_cam}) divisible by the group size ({world})")
-        self.rank, self.world, self.n_cam, self.group = rank, world, n_cam, group
-        self.n_local = n_cam // world
-
-    @property
-    def views(self) -> Tuple[int, int]:
-        return self.rank * self.n_local, (self.rank + 1) * self.n_local
-
-    def gathered_batch(self, sample: int, view: int, n_samples: int) -> int:
-        r, j = divmod(view, self.n_local)
-        return r * n_samples * self.n_local + sample * self.n_local + j
-
-    def kv_index(self, n_local_views: int, pairs: Sequence[Sequence[int]]) -> List[List[int]]:
-        assert n_local_views % self.n_local == 0 and len(pairs) == self.n_cam
-        n_samples = n_local_views // self.n_local
-        b, _ = self.views
-        return [[self.gathered_batch(s, pairs[b + j][0], n_samples), self.gathered_batch(s, pairs[b + j][1], n_samples)]
-                for s in range(n_samples) for j in range(self.n_local)]
-
-    def slice_views(self, inputs: dict) -> dict:
-        """Cut the view axis (dim 1) of camera_param / bboxes_3d_data / 5-D latents; per-scene tensors pass through."""
-        b, e = self.views
-        n_cam = self.n_cam
-
-        def cut(k, v):
-            if isinstance(v, dict):
-                return {kk: cut(kk, x) for kk, x in v.items()}
-            if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == n_cam and (k != "latents" or v.dim() == 5) \
-                    and k not in ("prompt_embeds", "negative_prompt_embeds", "image", "bev_map"):
-                return v[:, b:e]
-            return v
-        return {k: cut(k, v) for k, v in inputs.items()}
-
-    def all_gather_rows(self, t: torch.Tensor) -> torch.Tensor:
-        """[rows, cols] contiguous -> [world * rows, cols], rank-major, on the current stream."""
-        out = torch.empty((self.world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)
-        return out
-
-    def gather_views(self, local: torch.Tensor) -> torch.Tensor:
-        """(S, n_local, ...) per rank -> (S, n_cam, ...) on every rank."""
-        bufs = [torch.empty_like(local) for _ in range(self.world)]
-        dist.all_gather(bufs, local.contiguous(), group=self.group)
-        return torch.cat(bufs, dim=1)
-
-
 class ShardPlan:
     """How ONE scene's 12 guidance x view samples are spread over `world` ranks for low latency (BASELINE.json north_star,
     SURVEY.md section 8e).  Two independent cuts:
@@ -215,3 +160,85 @@ class ShardPlan:
                 return v[:, b:e]
             return v
         return {k: cut(k, v) for k, v in inputs.items()}
+
+
+class PeerGroup:
+    """A set of ranks of this node whose GPUs read each other's memory directly (NVLink peer memory through
+    torch.distributed._symmetric_memory): symmetric allocations, peer views of them, and a device-side barrier
+    (mdb_peer_barrier) — no NCCL collective on the data path.  `pg` must have been created on EVERY rank of the job
+    (dist.new_group is collective), see ShardContext."""
+
+    N_CHANNELS = 4
+
+    def __init__(self, ranks: Sequence[int], pg, device):
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self.ranks, self.pg, self.device = list(ranks), pg, device
+        self.rank = self.ranks.index(dist.get_rank())
+        self.world = len(self.ranks)
+        self.flags, self._flags_hdl = self.alloc((self.N_CHANNELS * self.world,), torch.int32)
+        self.flags.zero_()
+        self.epoch = torch.zeros(self.N_CHANNELS, dtype=torch.int32, device=device)
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=pg)  # every peer's flags are zero before the first device-side barrier
+
+    def alloc(self, shape, dtype):
+        """Symmetric tensor (same shape on every rank of the group) + its rendezvous handle."""
+        t = self._symm.empty(*shape, dtype=dtype, device=self.device)
+        return t, self._symm.rendezvous(t, self.pg)
+
+    def peer_view(self, hdl, peer: int, shape, dtype) -> torch.Tensor:
+        """Rank `peer`'s (group-relative) copy of a symmetric tensor as a tensor in THIS GPU's address space."""
+        return hdl.get_buffer(peer, tuple(shape), dtype)
+
+    def barrier(self, channel: int = 0, timeout_s: float = 5.0):
+        from . import ops
+        ops.peer_barrier(self._flags_hdl.buffer_ptrs_dev, self.rank, self.world, channel, self.N_CHANNELS, self.epoch,
+                         self.timed_out, timeout_s)
+
+    def check(self):
+        """Host-side: raise if a device-side barrier gave up waiting for a peer (call after a synchronize)."""
+        if int(self.timed_out.item()):
+            raise RuntimeError(f"mdb_peer_barrier timed out waiting for a peer GPU (group ranks {self.ranks})")
+
+
+class ShardContext:
+    """ShardPlan + the peer groups it needs: `half_group` (the ranks sharing one guidance half's views: K/V halo reads) and
+    `pair_group` (this rank and its partner in the other half: predicted-noise exchange for the guidance combine).  Create it
+    on every rank of the job at the same point (it creates process groups)."""
+
+    def __init__(self, n_cam: int, cfg: bool, pairs: Sequence[Sequence[int]], device, rank: Optional[int] = None,
+                 world: Optional[int] = None, peer_memory: bool = True):
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        self.plan = ShardPlan(rank, world, n_cam, cfg, pairs)
+        pl = self.plan
+        self.device = device
+        self.half_group = self.pair_group = None
+        halves = 2 if pl.split_cfg else 1
+        # dist.new_group is collective over the whole job: every rank creates every group, in the same order
+        half_pgs = [dist.new_group([h * pl.groups + g for g in range(pl.groups)]) for h in range(halves)] if pl.groups > 1 else []
+        pair_pgs = [dist.new_group([g, g + pl.groups]) for g in range(pl.groups)] if pl.split_cfg else []
+        if pl.groups > 1 and peer_memory:
+            self.half_group = PeerGroup(pl.half_ranks, half_pgs[pl.half], device)
+        if pl.split_cfg and peer_memory:
+            self.pair_group = PeerGroup(sorted([rank, pl.partner]), pair_pgs[pl.vg], device)
+        self._gather_pg = half_pgs[pl.half] if pl.groups > 1 else None
+
+    def gather_views(self, local: torch.Tensor) -> torch.Tensor:
+        """(S, n_local, ...) per rank of the half group -> (S, n_cam, ...) on every rank (uneven view counts allowed)."""
+        pl = self.plan
+        if pl.groups == 1:
+            return local
+        mx = max(pl.local_views_of(g) for g in range(pl.groups))
+        pad = torch.zeros((local.shape[0], mx, *local.shape[2:]), dtype=local.dtype, device=local.device)
+        pad[:, : local.shape[1]] = local
+        bufs = [torch.empty_like(pad) for _ in range(pl.groups)]
+        dist.all_gather(bufs, pad.contiguous(), group=self._gather_pg)
+        return torch.cat([bufs[g][:, : pl.local_views_of(g)] for g in range(pl.groups)], dim=1)
+
+    def check(self):
+        for g in (self.half_group, self.pair_group):
+            if g is not None:
+                g.check()

@@ -157,7 +157,8 @@ class _Net:
         self.resnets: List[arch.ResnetSpec] = [rs for b in self.down for rs, _ in b.layers] + [self.mid[0], self.mid[2]]
         self.transformers: List[arch.TransformerSpec] = [tr for b in self.down for _, tr in b.layers if tr] + [self.mid[1]]
         self._kv_idx = {}
-        self.view_shard = None  # dist.ViewShard when the cameras of a scene are split across ranks
+        self._kv_sym = {}
+        self.view_shard = None  # dist.ShardContext when the cameras of a scene are split across ranks
 
     # ---------------------------------------------------------------- time embedding
     def _finalize_specs(self):
@@ -212,22 +213,50 @@ class _Net:
         return FMap(out, x.n, x.h, x.w, rs.cout)
 
     def kv_index(self, n_views: int) -> torch.Tensor:
-        """[V, 2] int32: the two ring neighbours of each view inside its own scene (Nuscenes.yaml:27-33)."""
+        """[V, 2] int32: the two ring neighbours of each view inside its own scene (Nuscenes.yaml:27-33).  With the views
+        split across GPUs (dist.ShardContext) an entry is (source << 24) | batch, source 0 = this GPU's K/V buffer,
+        1 / 2 = the ring-neighbour GPUs' buffers (mdb_attention_multi)."""
         if n_views not in self._kv_idx:
             nb = self.cfg.neighboring_view_pair
             n_cam = len(nb)
-            if self.view_shard is not None:  # indices into the all-gathered K/V (dist.ViewShard)
-                idx = self.view_shard.kv_index(n_views, [nb[i] for i in range(n_cam)])
+            if self._sharded():
+                pl = self.view_shard.plan
+                assert n_views % pl.n_local == 0
+                _, idx = pl.kv_sources(n_views // pl.n_local)
+                idx = [[idx[2 * i], idx[2 * i + 1]] for i in range(n_views)]
             else:
                 assert n_views % n_cam == 0
                 idx = [[s * n_cam + nb[i][0], s * n_cam + nb[i][1]] for s in range(n_views // n_cam) for i in range(n_cam)]
             self._kv_idx[n_views] = torch.tensor(idx, dtype=torch.int32, device=self.device)
         return self._kv_idx[n_views]
 
+    def _sharded(self) -> bool:
+        return self.view_shard is not None and self.view_shard.plan.groups > 1
+
     def set_view_shard(self, shard) -> None:
-        """Split the cameras across ranks (dist.ViewShard) or back to all views on this GPU (None)."""
+        """Split the cameras across ranks (dist.ShardContext) or back to all views on this GPU (None)."""
         self.view_shard = shard
         self._kv_idx = {}
+        self._kv_sym = {}
+
+    def _neighbour_kv(self, key, V: int, L: int, C: int):
+        """This block's K/V buffer in symmetric memory and the ring-neighbour GPUs' copies of it, as attention sources."""
+        hit = self._kv_sym.get((key, V, L, C))
+        if hit is None:
+            sh = self.view_shard
+            pl, grp = sh.plan, sh.half_group
+            n_samples = V // pl.n_local
+            mx = max(pl.local_views_of(g) for g in range(pl.groups))
+            buf, hdl = grp.alloc((n_samples * mx * L, 2 * C), BF16)  # same shape on every rank (uneven view counts padded)
+            srcs, _ = pl.kv_sources(n_samples)
+            views = []
+            for g in srcs:
+                vg = n_samples * pl.local_views_of(g)
+                t = buf if g == pl.vg else grp.peer_view(hdl, g, (n_samples * mx * L, 2 * C), BF16)
+                views.append((t[: vg * L], vg))
+            hit = (buf[: V * L], hdl, views)
+            self._kv_sym[(key, V, L, C)] = hit
+        return hit[0], hit[2]
 
     def context_kv(self, ctx_bf16: torch.Tensor) -> Dict[str, torch.Tensor]:
         """attn2 K/V projections of the conditioning tokens for every transformer (step-invariant).
@@ -276,20 +305,24 @@ class _Net:
             if cfg.neighboring_attn_type != "add" or cfg.zero_module_type != "zero_linear":
                 raise NotImplementedError("only neighboring_attn_type='add' with the zero_linear connector (the shipped "
                                           "configs/model/SDv1.5mv_rawbox.yaml:19-20) is implemented")
-            if self.view_shard is None:
+            if not self._sharded():
                 wqkv, cq, sq = W.ln_lin(blk + ".attn4.lnqkv", blk + ".norm4",
                                         [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
                 qkv = ops.linear(X, wqkv, bias=cq, ln=sx, ln_colsum=sq)
                 o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V, heads=heads, lq=L, lk=L, d=d, ldq=3 * C,
                                   ldk=3 * C, ldv=3 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
             else:
-                # cameras split across ranks: local queries, K/V of every rank's views all-gathered over NVLink
+                # cameras split across GPUs: K/V of the local views go to a symmetric buffer; after one device-side
+                # barrier the attention kernel reads the two ring neighbours' K/V tiles IN PLACE from the neighbour
+                # GPUs over NVLink (TMA on peer-mapped addresses) while it works on the local tiles: no gather, no copy
                 wq, cq, sq = W.ln_lin(blk + ".attn4.lnq", blk + ".norm4", [blk + ".attn4.to_q"])
                 wkv, ckv, skv = W.ln_lin(blk + ".attn4.lnkv", blk + ".norm4", [blk + ".attn4.to_k", blk + ".attn4.to_v"])
                 q = ops.linear(X, wq, bias=cq, ln=sx, ln_colsum=sq)
-                kv = self.view_shard.all_gather_rows(ops.linear(X, wkv, bias=ckv, ln=sx, ln_colsum=skv))
-                o = ops.attention(q, kv, kv[:, C:], b=V, b_kv=V * self.view_shard.world, heads=heads, lq=L, lk=L, d=d,
-                                  ldq=C, ldk=2 * C, ldv=2 * C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
+                kv, srcs = self._neighbour_kv(blk, V, L, C)
+                ops.linear(X, wkv, bias=ckv, ln=sx, ln_colsum=skv, out=kv, ldo=2 * C)
+                self.view_shard.half_group.barrier(0)
+                o = ops.attention_multi(q, [(t, t[:, C:], 2 * C, vg) for t, vg in srcs], b=V, heads=heads, lq=L, lk=L, d=d,
+                                        ldq=C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
             wf, bf_ = W.folded_connector(blk)
             X, sx = ops.linear(o, wf, bias=bf_, residual=X, emit_stats=True)
         # --- GEGLU feed-forward

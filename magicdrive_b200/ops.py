@@ -212,7 +212,7 @@ def groupnorm(x0, c0, ld0, n_img, hw, gamma, beta, eps, silu, x1=None, c1=0, ld1
     global _launches
     _need_cuda(x0)
     out = torch.empty((n_img * hw, c0 + c1), dtype=BF16, device=x0.device)
-    stats = torch.empty((n_img * groups * 2,), dtype=F32, device=x0.device)
+    stats = torch.empty((max(n_img, 160) * groups * 2,), dtype=F32, device=x0.device)  # scratch: per-(image | CTA run) group partials
     check(_lib.lib().mdb_groupnorm(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n_img, hw, groups, float(eps), _ptr(gamma),
                                    _ptr(beta), int(silu), _ptr(out), c0 + c1, _ptr(stats), _stream()), "mdb_groupnorm")
     _launches += 2 if os.environ.get("MDB_GN_TWO_KERNEL") else 1  # one fused kernel (A/B: stats + apply)
@@ -254,6 +254,37 @@ def attention(q, k, v, *, b, heads, lq, lk, d, ldq, ldk, ldv, scale, kv_index=No
     _prof_end("attention", 4.0 * b * heads * lq * lk * d * n_sets, e0, f"B={b} H={heads} Lq={lq} Lk={lk} D={d} sets={n_sets}")
     _launches += 1
     return out
+
+
+def attention_multi(q, sources, *, b, heads, lq, lk, d, ldq, scale, kv_index, n_sets=1, out=None):
+    """Fused attention whose K/V batches live in up to three buffers (mdb_attention_multi).  `sources` = list of (k, v, ld, b_kv):
+    k / v are [b_kv * lk, >= heads*d] views with row stride ld (a peer GPU's buffer mapped through NVLink works like a local
+    one); kv_index entries are (source << 24) | batch index."""
+    global _launches
+    _need_cuda(q, *[t for s_ in sources for t in s_[:2]])
+    n = len(sources)
+    if out is None:
+        out = torch.empty((b * lq, heads * d), dtype=BF16, device=q.device)
+    ks = (C.c_void_p * n)(*[s_[0].data_ptr() for s_ in sources])
+    vs = (C.c_void_p * n)(*[s_[1].data_ptr() for s_ in sources])
+    ldk = (C.c_int * n)(*[int(s_[2]) for s_ in sources])
+    bkv = (C.c_int * n)(*[int(s_[3]) for s_ in sources])
+    e0 = _prof_begin()
+    check(_lib.lib().mdb_attention_multi(_ptr(q), ldq, n, ks, ldk, vs, ldk, bkv, _ptr(out), out.stride(0), b, heads, lq, lk, d,
+                                         _ptr(kv_index), n_sets, float(scale), _stream()), "mdb_attention_multi")
+    _prof_end("attention", 4.0 * b * heads * lq * lk * d * n_sets, e0, f"B={b} H={heads} Lq={lq} Lk={lk} D={d} sets={n_sets} src={n}")
+    _launches += 1
+    return out
+
+
+def peer_barrier(flag_ptrs_dev: int, rank: int, world: int, channel: int, n_channels: int, epoch, timed_out,
+                 timeout_s: float = 5.0):
+    """Device-side barrier over NVLink peer memory (mdb_peer_barrier); one warp on the current stream."""
+    global _launches
+    cycles = int(timeout_s * 1.9e9)
+    check(_lib.lib().mdb_peer_barrier(flag_ptrs_dev, rank, world, channel, n_channels, _ptr(epoch), cycles, _ptr(timed_out),
+                                      _stream()), "mdb_peer_barrier")
+    _launches += 1
 
 
 def add(a, b):

@@ -139,8 +139,8 @@ class BEVControlNetDenoiser:
     def __init__(self, unet: UNet2DConditionModelMultiview, controlnet: BEVControlNetModel, use_cuda_graph: bool = True,
                  overlap_controlnet: bool = True, view_shard=None, scheduler: str = "ddim", vae=None,
                  cfg_streams: bool = False):
-        """view_shard: a dist.ViewShard to split the cameras of each scene across the ranks of its group (inputs are
-        still passed with all n_cam views on every rank; the result is gathered back to (S, n_cam, ...)).
+        """view_shard: a dist.ShardContext to spread each scene's guidance halves x camera views over the ranks of the job
+        (inputs are still passed in full on every rank; the result is gathered back to (S, n_cam, ...)).
         scheduler: "ddim" (eta = 0) or "unipc" (the reference's default sampler, misc/test_utils.py:129).
         vae: a models.AutoencoderKL; enables output_type "pt" / "np" (decode_latents, pipeline_bev_controlnet.py:100-112).
         cfg_streams (opt-in, not yet measured): run the unconditional and the conditional half of the guidance batch as
@@ -187,10 +187,12 @@ class BEVControlNetDenoiser:
         if pin is not None and pin["mode"] == "change":
             # given views are re-noised from their clean latents at every step (pipeline_bev_controlnet_given_view.py:283-296)
             ops.pin_views(lat, pin["cond"], pin["noise0"], pin["coef_dev"], pin["mask"], h * w, c=lat.shape[1])
-        if self.cfg_streams and st["cfg"] and st.get("u_temb") is not None:
+        if self.cfg_streams and st["cfg"] and st["dup"] == 2 and st.get("u_temb") is not None:
             eps = self._step_models_cfg_streams(st, lat)
         else:
             eps = self._step_models(st, lat)
+        if st["cfg"] and st["dup"] == 1:
+            eps = self._exchange_guidance_halves(st, eps)
         if pin is not None and pin["mode"] == "once":
             # given views follow their own initial noise instead of the prediction (:379-389): overwrite both guidance
             # halves, so the combine u + s (c - u) returns exactly that noise
@@ -203,6 +205,22 @@ class BEVControlNetDenoiser:
         else:
             last, m0, m1 = st["hist"]
             ops.cfg_unipc_step(eps, lat, last, m0, m1, st["coef_dev"], st["cfg"], st["guidance"], c=lat.shape[1])
+
+    def _exchange_guidance_halves(self, st, eps):
+        """Guidance halves on two GPUs: each writes its predicted noise into its own AND its partner's [uncond ; cond] buffer
+        (symmetric memory, a direct NVLink store), so that after one device-side barrier both hold the pair and apply the
+        same guidance combine + scheduler update (pipeline_bev_controlnet.py:426-436) to their copy of the latents."""
+        grp, hf = self.view_shard.pair_group, self.view_shard.plan.half
+        npix = eps.shape[0]
+        if "eps2" not in st:
+            buf, hdl = grp.alloc((2 * npix, eps.shape[1]), F32)
+            st["eps2"] = (buf, grp.peer_view(hdl, 1 - grp.rank, (2 * npix, eps.shape[1]), F32), hdl)
+        mine, theirs, _ = st["eps2"]
+        grp.barrier(0)  # the partner has consumed the previous step's pair
+        mine[hf * npix:(hf + 1) * npix].copy_(eps)
+        theirs[hf * npix:(hf + 1) * npix].copy_(eps)
+        grp.barrier(1)  # both halves are in place on both GPUs
+        return mine
 
     def _step_models_cfg_streams(self, st, lat):
         """[uncond | cond] halves as two concurrent branches; returns eps fp32 [V*h*w, 8] (uncond rows first)."""
@@ -243,7 +261,7 @@ class BEVControlNetDenoiser:
         ue, ce = st["ue"], st["ce"]
         V, h, w = st["V"], st["h"], st["w"]
         # bf16, channel-padded to one K block; CFG: [uncond ; cond] share the latents (:352-354) -> repeat = 2
-        x = ops.pack_latents(lat, ue.CIN_PAD, repeat=2 if st["cfg"] else 1)
+        x = ops.pack_latents(lat, ue.CIN_PAD, repeat=st["dup"])
         if self.overlap_controlnet and st.get("u_temb") is not None:
             # The ControlNet and the UNet's down/mid path only meet at the skip additions: run them on two streams so
             # that each one's small-grid kernels and per-kernel tails are filled by the other (captured as two branches
@@ -286,10 +304,13 @@ class BEVControlNetDenoiser:
         if self.view_shard is not None:
             if latents.dim() == 4:
                 latents = torch.stack([latents] * camera_param.shape[1], dim=1)
-            cut = self.view_shard.slice_views(dict(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, latents=latents))
+            plan = self.view_shard.plan
+            if plan.cfg != cfg:
+                raise ValueError("the ShardContext was built for guidance " + ("on" if plan.cfg else "off"))
+            cut = plan.slice_views(dict(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, latents=latents))
             camera_param, bboxes_3d_data, latents = cut["camera_param"], cut["bboxes_3d_data"], cut["latents"]
             if conditional_latents is not None:
-                vb, ve = self.view_shard.views
+                vb, ve = plan.views
                 conditional_latents = [row[vb:ve] for row in conditional_latents]
         # ---- assemble the guidance batch where the inputs live (normally the host: a few small tensors), [uncond ; cond]
         camera_param = camera_param.to(F32)
@@ -308,12 +329,20 @@ class BEVControlNetDenoiser:
             image = torch.cat([kw["image"].to(image), image])
         else:
             text = prompt_embeds
+        dup = 2 if cfg else 1  # guidance halves batched on this GPU
+        if cfg and self.view_shard is not None and self.view_shard.plan.split_cfg:
+            # this rank runs ONE guidance half (0 = unconditional, 1 = conditional); the halves meet in the scheduler step
+            hf = self.view_shard.plan.half
+            camera_param, text, image = camera_param[hf * S:(hf + 1) * S], text[hf * S:(hf + 1) * S], image[hf * S:(hf + 1) * S]
+            if boxes is not None:
+                boxes = {k: v[hf * S:(hf + 1) * S] for k, v in boxes.items()}
+            dup = 1
         lat = latents.to(F32)
         if lat.dim() == 4:
             lat = torch.stack([lat] * n_cam, dim=1)
         S_, _, c, h, w = lat.shape
         lat_nhwc = lat.reshape(S * n_cam, c, h, w).permute(0, 2, 3, 1).contiguous().view(-1, c)
-        V = S * n_cam * (2 if cfg else 1)
+        V = S * n_cam * dup
         lc = 1 + text.shape[1] + (0 if boxes is None else boxes["bboxes"].shape[2])
         pin_mode, pin_mask, pin_cond = None, None, None
         if conditional_latents is not None and any(c is not None for row in conditional_latents for c in row):
@@ -331,7 +360,7 @@ class BEVControlNetDenoiser:
             inputs.update(pin_mask=pin_mask, pin_cond=pin_cond)
         # the resident state (and the captured graphs) hold pointers into the engines' packed weights: a rebuilt engine
         # (load_state_dict, .to(), BEVControlNetModel.prepare) must invalidate both
-        sig = (V, h, w, cfg, lc, S, n_cam, pin_mode, id(un.engine()), id(cn.engine()),
+        sig = (V, h, w, cfg, dup, lc, S, n_cam, pin_mode, id(un.engine()), id(cn.engine()),
                tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items())))
         st = self._static
         if st is not None and st["sig"] == sig:
@@ -355,7 +384,7 @@ class BEVControlNetDenoiser:
                 self._encode_conditions(st)
             return st
         dev_in = {k: v.to(dev) for k, v in inputs.items()}
-        st = dict(ue=un.engine(), ce=cn.engine(), V=V, h=h, w=w, S=S, n_cam=n_cam, cfg=cfg, sig=sig, inputs=dev_in,
+        st = dict(ue=un.engine(), ce=cn.engine(), V=V, h=h, w=w, S=S, n_cam=n_cam, cfg=cfg, dup=dup, sig=sig, inputs=dev_in,
                   guidance=float(guidance_scale), cond_scale=float(controlnet_conditioning_scale), latents=dev_in["latents"],
                   lc=lc, c_kv=None, u_kv=None, map=None,
                   t_dev=torch.zeros(V, dtype=F32, device=dev),
@@ -479,3 +508,8 @@ class BEVControlNetDenoiser:
         S, n_cam, h, w = st["S"], st["n_cam"], st["h"], st["w"]
         out = st["latents"].view(S, n_cam, h, w, -1).permute(0, 1, 4, 2, 3).contiguous()
         return out if self.view_shard is None else self.view_shard.gather_views(out)
+
+    def check_peers(self):
+        """Raise if a device-side peer barrier timed out (sharded mode; call after a synchronize)."""
+        if self.view_shard is not None:
+            self.view_shard.check()

@@ -51,66 +51,69 @@ def test_scene_sharding_world2_gloo():
     assert all(r[2] == 2.0 for r in res)
 
 
-# ---------------------------------------------------------------- view sharding (cameras of one scene across ranks)
+# ---------------------------------------------------------------- guidance-half x view sharding of ONE scene
 _PAIRS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}
 
 
-def test_view_shard_kv_index_addresses_the_gathered_neighbours():
-    from magicdrive_b200.dist import ViewShard
-    n_cam, n_samples, rows = 6, 4, 3  # samples = cfg halves x scenes
-    # global K/V stand-in: batch (s, g) holds the value 100*s + g in every row
-    glob = torch.tensor([[100.0 * s + g] * rows for s in range(n_samples) for g in range(n_cam)])
-    for world in (1, 2, 3, 6):
-        shards = [ViewShard(r, world, n_cam) for r in range(world)]
-        nl = n_cam // world
-        local = [glob.view(n_samples, n_cam, rows)[:, r * nl:(r + 1) * nl].reshape(-1, rows) for r in range(world)]
-        gathered = torch.cat(local)  # what all_gather_rows returns (rank-major)
-        for r, sh in enumerate(shards):
-            idx = sh.kv_index(n_samples * nl, [_PAIRS[i] for i in range(n_cam)])
-            assert len(idx) == n_samples * nl
-            for s in range(n_samples):
-                for j in range(nl):
-                    g = r * nl + j
-                    for side in range(2):
-                        assert gathered[idx[s * nl + j][side]][0].item() == 100.0 * s + _PAIRS[g][side]
+def test_shard_plan_covers_every_sample_once_and_addresses_the_right_neighbours():
+    from magicdrive_b200.dist import ShardPlan
+    n_cam, S, rows = 6, 2, 3
+    pairs = [_PAIRS[i] for i in range(n_cam)]
+    for cfg in (True, False):
+        for world in (1, 2, 3, 4, 6, 8, 12):
+            try:
+                plans = [ShardPlan(r, world, n_cam, cfg, pairs) for r in range(world)]
+            except ValueError:
+                assert (world // 2 if (cfg and world % 2 == 0) else world) > n_cam
+                continue
+            halves = 2 if plans[0].split_cfg else 1
+            # every (half, view) is owned by exactly one rank; partners own the same views in the other half
+            owned = sorted((p.half, v) for p in plans for v in range(*p.views))
+            assert owned == [(h, v) for h in range(halves) for v in range(n_cam)]
+            for p in plans:
+                assert plans[p.partner].views == p.views and (plans[p.partner].half != p.half) == p.split_cfg
+                assert max(q.n_local for q in plans) - min(q.n_local for q in plans) <= 1
+            # K/V stand-in per rank of a half: batch (s, local view j) holds 100*s + global view
+            n_samples = S * (1 if plans[0].split_cfg else (2 if cfg else 1))
+            for p in plans:
+                group = [q for q in plans if q.half == p.half]
+                bufs = {q.vg: torch.tensor([[100.0 * s + q.views[0] + j] * rows for s in range(n_samples) for j in range(q.n_local)])
+                        for q in group}
+                srcs, idx = p.kv_sources(n_samples)
+                assert srcs[0] == p.vg and len(srcs) <= 3 and len(idx) == 2 * n_samples * p.n_local
+                for s in range(n_samples):
+                    for j in range(p.n_local):
+                        for side in range(2):
+                            e = idx[(s * p.n_local + j) * 2 + side]
+                            got = bufs[srcs[e >> 24]][e & 0xffffff][0].item()
+                            assert got == 100.0 * s + _PAIRS[p.views[0] + j][side]
 
 
-def _view_worker(rank, world, port, q):
-    from magicdrive_b200.dist import ViewShard
+def _gather_worker(rank, world, port, q):
+    from magicdrive_b200.dist import ShardContext
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    full = synthetic_inputs(2, 6, 4, 6, n_box=3, map_hw=8, seed=7)
-    sh = ViewShard(rank, world, 6)
-    lat5 = torch.stack([full["latents"]] * 6, dim=1) + torch.arange(6.0).view(1, 6, 1, 1, 1)
-    mine = sh.slice_views(dict(camera_param=full["camera_param"], bboxes_3d_data=full["bboxes_3d_data"], latents=lat5,
-                               prompt_embeds=full["prompt_embeds"]))
-    b, e = sh.views
-    ok = mine["camera_param"].shape[1] == e - b and mine["bboxes_3d_data"]["masks"].shape[1] == e - b
-    ok &= mine["prompt_embeds"].shape == full["prompt_embeds"].shape and torch.equal(mine["latents"], lat5[:, b:e])
-    # "cross-view attention" stand-in: out(view) = x(view) + mean of the two neighbours' K rows, K = 3 * x
-    S, nl = 2, e - b
-    x_loc = mine["latents"].reshape(S * nl, -1)
-    kv = sh.all_gather_rows((3.0 * x_loc).contiguous())
-    idx = torch.tensor(sh.kv_index(S * nl, [_PAIRS[i] for i in range(6)]))
-    out_loc = x_loc + 0.5 * (kv[idx[:, 0]] + kv[idx[:, 1]])
-    out = sh.gather_views(out_loc.view(S, nl, -1))
-    xg = lat5.reshape(S, 6, -1)
-    nb = torch.tensor([_PAIRS[i] for i in range(6)])
-    ref = xg + 0.5 * (3.0 * xg[:, nb[:, 0]] + 3.0 * xg[:, nb[:, 1]])
-    ok &= torch.equal(out, ref)
+    ctx = ShardContext(6, False, [_PAIRS[i] for i in range(6)], "cpu", peer_memory=False)  # 4 ranks, views 2+2+1+1
+    pl = ctx.plan
+    full = torch.arange(2 * 6 * 5, dtype=torch.float32).view(2, 6, 5)
+    mine = pl.slice_views(dict(latents=full.view(2, 6, 5, 1, 1).expand(-1, -1, -1, 1, 1).contiguous(), camera_param=full))
+    ok = torch.equal(mine["camera_param"], full[:, pl.views[0]:pl.views[1]])
+    out = ctx.gather_views(mine["camera_param"].contiguous())
+    ok &= torch.equal(out, full)
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, bool(ok)))
+    q.put((rank, bool(ok), pl.views))
 
 
-def test_view_sharding_world2_gloo():
+def test_uneven_view_gather_world4_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_view_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gather_worker, args=(r, 4, port, q)) for r in range(4)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
+    res = sorted(q.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(60)
-    assert [r[1] for r in res] == [True, True]
+    assert [r[1] for r in res] == [True] * 4
+    assert [r[2] for r in res] == [(0, 2), (2, 4), (4, 5), (5, 6)]

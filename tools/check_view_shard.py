@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Parity of the view-sharded mode (cameras of a scene split across GPUs + NCCL all-gather of cross-view K/V)
-against the unsharded path on the same inputs.  Launch:
+"""Parity of the sharded low-latency mode (one scene's guidance halves x camera views spread over the GPUs, neighbour K/V and
+the partner half's noise exchanged through NVLink peer memory) against the unsharded path on the same inputs.  Launch:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/check_view_shard.py
 Prints one line per rank; exits non-zero when the sharded result drifts from the single-GPU one."""
 import os
@@ -13,7 +13,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from magicdrive_b200 import arch  # noqa: E402
-from magicdrive_b200.dist import ViewShard, shutdown  # noqa: E402
+from magicdrive_b200.dist import ShardContext, shutdown  # noqa: E402
 from magicdrive_b200.models import BEVControlNetModel, UNet2DConditionModelMultiview  # noqa: E402
 from magicdrive_b200.pipeline import BEVControlNetDenoiser  # noqa: E402
 from magicdrive_b200.synthetic import synthetic_inputs  # noqa: E402
@@ -34,15 +34,19 @@ def main():
     ref = BEVControlNetDenoiser(un, cn, use_cuda_graph=False)(**kw)
     rc = 0
     dens = []
+    ctx = ShardContext(6, True, [arch.DEFAULT_NEIGHBORS[i] for i in range(6)], dev)
+    print(f"[view-shard] rank {rank}: half {ctx.plan.half} views {ctx.plan.views} partner {ctx.plan.partner}", flush=True)
     for graph in (False, True):
-        den = BEVControlNetDenoiser(un, cn, use_cuda_graph=graph, view_shard=ViewShard(rank, world, 6))
+        den = BEVControlNetDenoiser(un, cn, use_cuda_graph=graph, view_shard=ctx)
         dens.append(den)
         out = den(**kw)
+        torch.cuda.synchronize()
+        den.check_peers()
         err = ((out - ref).norm() / ref.norm()).item()
         ok = out.shape == ref.shape and err < 2e-2
         print(f"[view-shard] rank {rank}/{world} graph={graph} rel-L2 vs unsharded {err:.3e} {'OK' if ok else 'FAIL'}", flush=True)
         rc |= 0 if ok else 1
-    un.engine().set_view_shard(None)
+    un.set_view_shard(None)
     sys.stdout.flush()
     if rc:
         os._exit(rc)

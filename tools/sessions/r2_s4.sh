@@ -15,7 +15,7 @@ MDB_GEMM_VARIANT=2 timeout 200 python tools/bench_gemm.py --warm > $O/warm_tc2.l
 MDB_GEMM_VARIANT=4 timeout 200 python tools/bench_gemm.py --warm > $O/warm_single_g4.log 2>&1
 MDB_GEMM_VARIANT=3 timeout 120 python tools/bench_gemm.py --trace --warm --only tok16800_320x > $O/trace_pair_warm.log 2>&1
 timeout 120 python tools/bench_attn.py --trace > $O/attn_trace.log 2>&1
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > $O/pytest_gpu.log
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > $O/pytest_gpu.log
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference > $O/bench_full.json 2> $O/bench_full.err
 for g in epi2 epi3; do
   MDB_LIB_PATH=$V/lib$g.so timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference > $O/bench_full_$g.json 2> $O/bench_full_$g.err
@@ -31,3 +31,10 @@ except Exception as e: print('ERR', e)
 MDB_GEMM_VARIANT=3 timeout 600 ncu --profile-from-start off --set full --import-source on --clock-control none --cache-control none \
   -k regex:gemm_pair -o $O/prof_pair python tools/bench_gemm.py --profile --warm --only tok16800 > $O/ncu_pair.log 2>&1
 tail -3 $O/ncu_pair.log
+# cooperative pixel-major GroupNorm (opt-in): correctness, then the whole step with it
+MDB_GN_GRID=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k groupnorm 2>&1 | tail -4 > $O/gn_grid_tests.log
+MDB_GN_GRID=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference > $O/bench_full_gngrid.json 2> $O/bench_full_gngrid.err
+MDB_GN_GRID=1 timeout 600 ncu --profile-from-start off --cache-control none --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_step_gngrid.csv python tools/profile_step.py --workload full > $O/ncu_step_gngrid.log 2>&1
+tail -3 $O/gn_grid_tests.log; python -c "
+import json
+d=json.loads(open('$O/bench_full_gngrid.json').read().strip().splitlines()[-1]); print('gn grid step', d['ms_per_step'])"
