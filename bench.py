@@ -48,8 +48,8 @@ def parse():
                     help="sampler fused into the step: ddim (BASELINE.json configs: 50-step DDIM) or unipc (the reference's default)")
     ap.add_argument("--cfg-streams", action="store_true",
                     help="opt-in: run the unconditional / conditional guidance halves as two concurrent graph branches")
-    ap.add_argument("--decode", action="store_true",
-                    help="also time the VAE decode of the scene's 6 views (SURVEY.md section 8 f2) and report it as vae_decode")
+    ap.add_argument("--no-decode", action="store_true",
+                    help="skip timing the VAE decode of the scene's 6 views (SURVEY.md section 8 f2, reported as vae_decode)")
     ap.add_argument("--shard", default="scenes", choices=["scenes", "views"],
                     help="N>1: scenes = independent scenes per GPU (default, weak scaling, no data-path collective); "
                          "views = the 6 cameras of the SAME scenes split across GPUs with an exchange of the "
@@ -438,11 +438,11 @@ def main():
                                        "call instead of every step; executed = tensor-core FLOPs the step actually launches"}}
 
     vae_decode = None
-    if args.decode:
+    if not args.no_decode and not by_views:
         from magicdrive_b200.models import AutoencoderKL
         vae = AutoencoderKL(**asdict(arch.VaeConfig())).reset_parameters_synthetic(13).to(dev, torch.bfloat16)
         lat5 = pipe.latents_out(st) * 0.18215
-        for _ in range(2):
+        for _ in range(3):
             vae.decode_latents(lat5)
         barrier()
         e0.record()
@@ -451,7 +451,10 @@ def main():
         e1.record()
         barrier()
         vae_decode = {"ms_per_scene": e0.elapsed_time(e1) / 5 / args.scenes, "views": 6,
-                      "note": "AutoencoderKL.decode_latents of the 6 views at full resolution, SD-1.5 VAE config, random-init weights"}
+                      "note": "AutoencoderKL.decode_latents of the 6 views at full resolution (one CUDA-graph replay per call, latents "
+                              "in / images out on the device), SD-1.5 VAE config, random-init weights; not part of `value`"}
+        del vae
+        torch.cuda.empty_cache()
 
     if rank == 0:
         cpu, gpu_ref = None, None

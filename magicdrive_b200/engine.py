@@ -561,17 +561,20 @@ class VaeDecoderEngine:
         q = ops.linear(t, wq, bias=bq)
         k = ops.linear(t, wk, bias=bk)
         lp = (L + 63) // 64 * 64  # keys padded to whole K blocks of the P.V product
-        o = torch.empty((x.n * L, C), dtype=q.dtype, device=q.device)
+        # persistent scratch (no per-call allocation or zero-fill: the decode is captured in a CUDA graph): scores and
+        # probabilities [L, lp] per image, V^T [C, lp] whose pad columns stay zero from allocation (P is zero there too)
+        key = ("vae_attn", x.n, L, C)
+        if key not in W.t:
+            dev = q.device
+            W.t[key] = (torch.empty((x.n, L, lp), dtype=F32, device=dev), torch.zeros((x.n, C, lp), dtype=q.dtype, device=dev),
+                        torch.empty((x.n * L, C), dtype=q.dtype, device=dev))
+        sbuf, vtbuf, o = W.t[key]
         for i in range(x.n):
             rows = slice(i * L, (i + 1) * L)
-            kp = torch.zeros((lp, C), dtype=k.dtype, device=k.device)
-            kp[:L] = k[rows]
-            tp = torch.zeros((lp, C), dtype=t.dtype, device=t.device)
-            tp[:L] = t[rows]
-            s = ops.linear(q[rows], kp, out_f32=True, out_scale=C ** -0.5)          # [L, lp]: q . k_j / sqrt(C)
-            p = ops.softmax_rows(s, L, lp)                                          # bf16, padded keys get 0
-            vt = ops.linear(wv, tp)                                                 # [C, lp] = W_v X^T  (V^T, no bias)
-            ops.linear(p, vt, bias=bv, out=o[rows], ldo=C)                           # P V + b_v (rows of P sum to 1)
+            ops.linear(q[rows], k[rows], out_f32=True, out_scale=C ** -0.5, out=sbuf[i], ldo=lp)   # [L, L]: q . k_j / sqrt(C)
+            p = ops.softmax_rows(sbuf[i], L, lp)                                                    # bf16, padded keys get 0
+            ops.linear(wv, t[rows], out=vtbuf[i], ldo=lp)                                           # [C, L] = W_v X^T  (V^T, no bias)
+            ops.linear(p, vtbuf[i], bias=bv, out=o[rows], ldo=C)                                    # P V + b_v (rows of P sum to 1)
         wo, bo = W.lin(a + ".to_out.0")
         out = ops.linear(o, wo, bias=bo, residual=x.data)
         return FMap(out, x.n, x.h, x.w, C)

@@ -441,8 +441,14 @@ class AutoencoderKL(_B200Module):
             sd[k] = v
         return super().load_state_dict(sd, strict=strict, **kw)
 
+    use_cuda_graph = True  # decode_latents replays one captured graph per shape
+    _decode_graphs: dict = {}
+
     def engine(self) -> VaeDecoderEngine:
-        return self._get_engine(VaeDecoderEngine)
+        eng = self._get_engine(VaeDecoderEngine)
+        if getattr(self, "_graphs_for", None) is not eng:  # weights changed -> engine rebuilt -> graphs stale
+            self._decode_graphs, self._graphs_for = {}, eng
+        return eng
 
     def encode(self, *a, **k):
         raise NotImplementedError("AutoencoderKL.encode is not on the generation path (SURVEY.md §2.1); only decode is built")
@@ -461,5 +467,24 @@ class AutoencoderKL(_B200Module):
         1/scaling_factor, image/2+0.5 and clamp folded into the first and last convolution: (b, n_cam, 8h, 8w, 3) fp32."""
         b, n_cam, c, h, w = latents.shape
         z = latents.to(self.device, F32).permute(0, 1, 3, 4, 2).contiguous().view(-1, c)
-        img = self.engine().decode(z, b * n_cam, h, w, scale=1.0 / self.config["scaling_factor"], to_unit_range=True)
+        eng = self.engine()
+        run = lambda zz: eng.decode(zz, b * n_cam, h, w, scale=1.0 / self.config["scaling_factor"], to_unit_range=True)
+        if not (self.use_cuda_graph and z.is_cuda):
+            img = run(z)
+        else:
+            # the decode of a given shape is one CUDA graph on resident input / output buffers (eager once to size scratch)
+            key = (id(eng), b * n_cam, h, w)
+            g = self._decode_graphs.get(key)
+            if g is None:
+                zin = z.clone()
+                run(zin)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = run(zin)
+                g = self._decode_graphs[key] = (graph, zin, out)
+            graph, zin, out = g
+            zin.copy_(z)
+            graph.replay()
+            img = out.clone()
         return img.reshape(b, n_cam, *img.shape[1:])
