@@ -217,13 +217,55 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&s_full[s], static_cast<uint32_t>(it / NBUF) & 1u);
         tc_fence_after();
         if (tslot > 0) MDB_ATRACE(tslot, it, 1);
+        const int nval = p.lk - (j * ATT_BN + hlf * 64);  // valid keys among this thread's 64 columns
+        const bool tail = nval < 64;
+        float rs = 0.f;
+        uint32_t pk[32];
+        bool done = false;
+#ifndef MDB_ATTN_NO_PIPELINED_SOFTMAX
+        if (!tail && j > 0) {
+          // ---- speculative fast path (every tile but the first and a ragged last one): the S row is read from tensor
+          // memory in four 16-column pieces, piece i+1 in flight while piece i goes through the exponentials, using the
+          // CURRENT reference maximum.  TMEM read bandwidth and the MUFU are the two comparable costs of a tile; reading
+          // all 64 columns first (below) runs them back to back in every warp at the same time.  The guess "no element
+          // exceeds m_ref + 2^8" is checked piece by piece; a miss (rare once the maximum has settled) falls through to
+          // the exact path, which re-reads S (P is only written after the last piece).  Same m_ref, same arithmetic:
+          // bit-identical to the exact path.
+          uint32_t a[16], b[16];
+          tmem_ld_32x16(tmem_s, a);
+          tmem_ld_wait();
+          bool ok = true;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t(&cur)[16] = (c & 1) ? b : a;
+            uint32_t(&nxt)[16] = (c & 1) ? a : b;
+            if (c < 3) tmem_ld_32x16(tmem_s + 16 * (c + 1), nxt);
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(cur[i]));
+            const float cm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+            ok = ok && !(cm > m_ref + ATT_LAZY_LOG2);
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = exp2f(fmaf(__uint_as_float(cur[i]), sc, -m_ref));
+              const float p1 = exp2f(fmaf(__uint_as_float(cur[i + 1]), sc, -m_ref));
+              rs += p0 + p1;
+              pk[8 * c + (i >> 1)] = pack_bf16(p0, p1);
+            }
+            if (c < 3) tmem_ld_wait();
+          }
+          done = !__any_sync(0xffffffffu, !ok);
+          if (tslot > 0) MDB_ATRACE(tslot, it, 2);
+          if (tslot > 0) MDB_ATRACE(tslot, it, 3);
+        }
+#endif
+        if (!done) {
+        rs = 0.f;
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(tmem_s, v0);
         tmem_ld_32x32(tmem_s + 32, v1);
         tmem_ld_wait();
         if (tslot > 0) MDB_ATRACE(tslot, it, 2);
-        const int nval = p.lk - (j * ATT_BN + hlf * 64);  // valid keys among this thread's 64 columns
-        const bool tail = nval < 64;
         float mx = -INFINITY;
         if (!tail) {
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
@@ -261,8 +303,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (need) m_ref = m_new;
         }
         // ---- p = exp2(s*sc - m_ref), row sum, bf16 pairs over the first 32 of the own 64 S columns
-        float rs = 0.f;
-        uint32_t pk[32];
         if (!tail) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -285,6 +325,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             pk[i >> 1] = pack_bf16(p0, p1);
             pk[16 + (i >> 1)] = pack_bf16(p2, p3);
           }
+        }
         }
         if (tslot > 0) MDB_ATRACE(tslot, it, 4);
         tmem_st_32x16(tmem_s, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
