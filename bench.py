@@ -54,6 +54,9 @@ def parse():
                     help="N>1: scenes = independent scenes per GPU (default, weak scaling, no data-path collective); "
                          "views = the 6 cameras of the SAME scenes split across GPUs with an exchange of the "
                          "cross-view K/V per multiview block (strong scaling, latency mode)")
+    ap.add_argument("--strong-scaling", action="store_true",
+                    help="N>1, default sharding: after the replica measurement also time ONE scene spread over all N GPUs "
+                         "(guidance halves x views through NVLink peer memory) and report it as `strong_scaling`")
     return ap.parse_args()
 
 
@@ -456,6 +459,39 @@ def main():
         del vae
         torch.cuda.empty_cache()
 
+    strong = None
+    if world > 1 and not by_views and (args.strong_scaling or os.environ.get("MDB_BENCH_STRONG") == "1"):
+        # the same scene on all N GPUs: latency mode; every rank runs its share, time = max over ranks
+        from magicdrive_b200.dist import ShardContext
+        ctx = ShardContext(6, True, [ucfg.neighboring_view_pair[i] for i in range(6)], dev)
+        pipe.release_graph()
+        pipe2 = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph, overlap_controlnet=not args.no_overlap,
+                                      view_shard=ctx, scheduler=args.scheduler)
+        inp0, _, _ = make_inputs(args, 0)
+        st2 = pipe2.prepare(inp0["latents"], inp0["prompt_embeds"], inp0["negative_prompt_embeds"], inp0["camera_param"],
+                            inp0["bboxes_3d_data"], inp0["bev_map"], guidance_scale=2.0)
+        pipe2.set_schedule(st2, 50)
+        for i in range(max(3, args.warmup)):
+            pipe2.run_steps(st2, i, i + 1)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            pipe2.run_steps(st2, (3 + i) % 50, (3 + i) % 50 + 1)
+        e1.record()
+        barrier()
+        pipe2.check_peers()
+        tt = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        strong = {"ms_per_step": tt.item(), "scenes": args.scenes, "value": args.scenes / (tt.item() * 1e-3), "unit": "scene-steps/s",
+                  "speedup_vs_one_gpu_step": ms_step / tt.item(),
+                  "layout": f"guidance halves x camera views over {world} GPUs: this rank half {ctx.plan.half}, views {list(ctx.plan.views)}",
+                  "note": "one scene's 12 guidance x view samples spread over all GPUs; neighbour K/V and the partner half's noise "
+                          "through NVLink peer memory (mdb_attention_multi / mdb_peer_barrier), no NCCL on the data path; "
+                          "speed-up is against this run's own one-scene-per-GPU step time"}
+        un.set_view_shard(None)
+        pipe2.release_graph()
+        pipe = pipe2  # torn down below
+
     if rank == 0:
         cpu, gpu_ref = None, None
         if n_gpus == 1 and not (args.no_cpu_baseline and args.no_gpu_reference):
@@ -491,6 +527,8 @@ def main():
                             "cfg_streams": bool(args.cfg_streams)}}
         if vae_decode is not None:
             line["vae_decode"] = vae_decode
+        if strong is not None:
+            line["strong_scaling"] = strong
         print(json.dumps(line))
     if world > 1:
         from magicdrive_b200.dist import shutdown

@@ -44,3 +44,7 @@ timeout 120 python tools/bench_attn.py tc2 tc2d > $O/bench_attn_pipe.log 2>&1
 MDB_LIB_PATH=$V/libnopipe.so timeout 120 python tools/bench_attn.py tc2 tc2d > $O/bench_attn_nopipe.log 2>&1
 MDB_LIB_PATH=$V/libnopipe.so timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-decode > $O/bench_full_nopipe.json 2> $O/bench_full_nopipe.err
 tail -3 $O/attn_tests.log; cat $O/bench_attn_pipe.log $O/bench_attn_nopipe.log
+timeout 900 python bench.py --steps 20 --warmup 3 > $O/bench_full_with_refs.json 2> $O/bench_full_with_refs.err
+tail -2 $O/bench_full_with_refs.err; python -c "
+import json
+d=json.loads(open('$O/bench_full_with_refs.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['gpu_reference'], d['cpu_baseline'], d.get('vae_decode'), d['e2e_full_reencode'])"
