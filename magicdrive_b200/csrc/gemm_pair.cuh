@@ -72,6 +72,21 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// explicit shared-space accesses (the staging / constant buffers are carved from a re-aligned dynamic-smem pointer, for which
+// the compiler would otherwise emit generic LD / ST); volatile keeps them ordered against the mbarrier / tcgen05 waits
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ unsigned long long bf2_to_f2(uint32_t r) { return pk2u(r << 16, r & 0xffff0000u); }
 __device__ __forceinline__ uint32_t f2_to_bf2(unsigned long long v) {
   float a, b;
@@ -370,7 +385,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int rem = row - li * box_hw;
     const int lh = rem / p.bw;
     const int lw = rem - lh * p.bw;
-    uint8_t* const my_row = smO + row * 64;         // this thread's 64-byte row inside a staging box
+    const uint32_t my_row = smem_u32(smO) + row * 64;  // this thread's 64-byte row inside a staging box (shared-space address)
+    const uint32_t smC_u32 = smem_u32(smC);
     const int swz = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk j sits at j ^ swz
     const bool has_ln = pp.ln_stats != nullptr;
     const float scale = p.out_scale;
@@ -432,7 +448,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const long long pix = row_pix(t, row_ok);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const float* cst = smC + as * 512;
+      const uint32_t cst = smC_u32 + as * 2048;  // [bias + shift | colsum] fp32 x 256 each
       // this tile's row scalars from the prefetched statistics
       float rowA = scale, rowB = 0.f;
       if (has_ln) {
@@ -466,34 +482,34 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int c = 0; c < nch; ++c, ++gk) {
         if ((c % G) != eg) continue;
         const int buf = gk % NBUF;
-        uint8_t* const srow = my_row + buf * Cfg::kBufBytes;
+        const uint32_t srow = my_row + buf * Cfg::kBufBytes;
         if (!geglu) {
           uint32_t v[32];
           tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while we wait for the staging box
           mbar_wait(&res_full[buf], (gk / NBUF) & 1);
-          const float4* cb4 = reinterpret_cast<const float4*>(cst + c * 32);
+          const uint32_t cb = cst + c * 128;
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b0 = cb4[2 * j], b1 = cb4[2 * j + 1];
+            const float4 b0 = lds_f4(cb + 32 * j), b1 = lds_f4(cb + 32 * j + 16);
             unsigned long long t0 = pk2(b0.x, b0.y), t1 = pk2(b0.z, b0.w), t2 = pk2(b1.x, b1.y), t3 = pk2(b1.z, b1.w);
             if (has_ln) {
-              const float4 s0 = cb4[64 + 2 * j], s1 = cb4[64 + 2 * j + 1];
+              const float4 s0 = lds_f4(cb + 1024 + 32 * j), s1 = lds_f4(cb + 1024 + 32 * j + 16);
               t0 = fma2(B2, pk2(s0.x, s0.y), t0), t1 = fma2(B2, pk2(s0.z, s0.w), t1);
               t2 = fma2(B2, pk2(s1.x, s1.y), t2), t3 = fma2(B2, pk2(s1.z, s1.w), t3);
             }
             unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), t0), o1 = fma2(A2, pk2u(v[8 * j + 2], v[8 * j + 3]), t1);
             unsigned long long o2 = fma2(A2, pk2u(v[8 * j + 4], v[8 * j + 5]), t2), o3 = fma2(A2, pk2u(v[8 * j + 6], v[8 * j + 7]), t3);
-            uint4* const slot = reinterpret_cast<uint4*>(srow + ((j ^ swz) << 4));
+            const uint32_t slot = srow + ((j ^ swz) << 4);
             if (pp.use_res_tma) {
-              const uint4 r = *slot;
+              const uint4 r = lds_u4(slot);
               o0 = add2(o0, bf2_to_f2(r.x)), o1 = add2(o1, bf2_to_f2(r.y)), o2 = add2(o2, bf2_to_f2(r.z)), o3 = add2(o3, bf2_to_f2(r.w));
             }
             if (pp.stats_out) {
               st_s2 = add2(add2(st_s2, add2(o0, o1)), add2(o2, o3));
               st_ss2 = fma2(o0, o0, fma2(o1, o1, fma2(o2, o2, fma2(o3, o3, st_ss2))));
             }
-            *slot = make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3));
+            sts_u4(slot, make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3)));
           }
         } else {
           constexpr int HALF = BLOCK_N / 2;
@@ -503,18 +519,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t v[16], g[16];
             tmem_ld_32x16(lane_addr + c * 32 + hh * 16, v);
             tmem_ld_32x16(lane_addr + HALF + c * 32 + hh * 16, g);
-            const float4* cv4 = reinterpret_cast<const float4*>(cst + c * 32 + hh * 16);
-            const float4* cg4 = reinterpret_cast<const float4*>(cst + HALF + c * 32 + hh * 16);
+            const uint32_t cv = cst + (c * 32 + hh * 16) * 4;
+            const uint32_t cg = cst + (HALF + c * 32 + hh * 16) * 4;
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               unsigned long long o[4];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const float4 bv = cv4[2 * j + e], bg = cg4[2 * j + e];
+                const float4 bv = lds_f4(cv + (2 * j + e) * 16), bg = lds_f4(cg + (2 * j + e) * 16);
                 unsigned long long tv0 = pk2(bv.x, bv.y), tv1 = pk2(bv.z, bv.w), tg0 = pk2(bg.x, bg.y), tg1 = pk2(bg.z, bg.w);
                 if (has_ln) {
-                  const float4 sv = cv4[64 + 2 * j + e], sg = cg4[64 + 2 * j + e];
+                  const float4 sv = lds_f4(cv + 1024 + (2 * j + e) * 16), sg = lds_f4(cg + 1024 + (2 * j + e) * 16);
                   tv0 = fma2(B2, pk2(sv.x, sv.y), tv0), tv1 = fma2(B2, pk2(sv.z, sv.w), tv1);
                   tg0 = fma2(B2, pk2(sg.x, sg.y), tg0), tg1 = fma2(B2, pk2(sg.z, sg.w), tg1);
                 }
@@ -524,8 +540,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 o[2 * e] = mul2(a0, gelu_erf2(g0));
                 o[2 * e + 1] = mul2(a1, gelu_erf2(g1));
               }
-              *reinterpret_cast<uint4*>(srow + (((hh * 2 + j) ^ swz) << 4)) =
-                  make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3]));
+              sts_u4(srow + (((hh * 2 + j) ^ swz) << 4), make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3])));
             }
           }
         }
