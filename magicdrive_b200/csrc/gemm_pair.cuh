@@ -320,49 +320,56 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // =========================== staging-buffer manager: residual loads + output stores (one lane) ==============
     if (lane == 0) {
       const uint32_t box_bytes = static_cast<uint32_t>(p.bn * p.bh * p.bw) * 64;
-      // two cursors over the same (tile, chunk) sequence: `pre` prepares buffers kAhead chunks ahead of `sto`
-      int pre_t = cluster_id, pre_c = 0, pre_k = 0;
-      int sto_t = cluster_id, sto_c = 0, sto_k = 0;
-      auto chunks_of = [&](int t) {
-        const int nt = t / pp.m_groups;
-        const int left = (pp.out_cols - nt * out_per_tile) / 32;
-        return left < ch_tile ? left : ch_tile;
+      // two cursors over the same (tile, chunk) sequence: `pre` prepares buffers kAhead chunks ahead of `sto`.  The tile
+      // coordinates of a cursor are recomputed only when it moves to another tile (this single thread must keep up with
+      // one TMA store + one TMA load per 32-column chunk).
+      struct Cursor {
+        int t, c, k, nch, col0, w0, h0, img0;
+        bool real;
       };
-      auto coords = [&](int t, int c, int& col0, int& w0, int& h0, int& img0) {
-        const int mg = t % pp.m_groups;
-        const int nt = t / pp.m_groups;
+      auto enter_tile = [&](Cursor& cu) {
+        if (cu.t >= total) return;
+        const int mg = cu.t % pp.m_groups;
+        const int nt = cu.t / pp.m_groups;
         const int mt = mg * CTAS + static_cast<int>(rank);
-        col0 = nt * out_per_tile + c * 32;
-        w0 = (mt % p.tiles_w) * p.bw;
-        h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
-        img0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-        return mt < pp.m_tiles;
+        const int left = (pp.out_cols - nt * out_per_tile) / 32;
+        cu.nch = left < ch_tile ? left : ch_tile;
+        cu.col0 = nt * out_per_tile;
+        cu.w0 = (mt % p.tiles_w) * p.bw;
+        cu.h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        cu.img0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+        cu.real = mt < pp.m_tiles;
+        cu.c = 0;
       };
-      auto prepare = [&]() {  // make staging box pre_k ready for the epilogue
-        const int buf = pre_k % NBUF;
-        if (pre_k >= NBUF) bulk_wait_group_read<NBUF - Cfg::kAhead - 1>();  // the store that last used `buf` has read it
-        int col0, w0, h0, img0;
-        const bool real = coords(pre_t, pre_c, col0, w0, h0, img0);
-        if (pp.use_res_tma && real) {
+      auto advance = [&](Cursor& cu) {
+        ++cu.k;
+        if (++cu.c == cu.nch) {
+          cu.t += n_clusters;
+          enter_tile(cu);
+        }
+      };
+      Cursor pre{cluster_id, 0, 0, 0, 0, 0, 0, 0, false}, sto{cluster_id, 0, 0, 0, 0, 0, 0, 0, false};
+      enter_tile(pre);
+      enter_tile(sto);
+      auto prepare = [&]() {  // make staging box pre.k ready for the epilogue
+        const int buf = pre.k % NBUF;
+        if (pre.k >= NBUF) bulk_wait_group_read<NBUF - Cfg::kAhead - 1>();  // the store that last used `buf` has read it
+        if (pp.use_res_tma && pre.real) {
           mbar_arrive_expect_tx(&res_full[buf], box_bytes);
-          tma_load_4d(&tmRes, &res_full[buf], smO + buf * Cfg::kBufBytes, col0, w0, h0, img0);
+          tma_load_4d(&tmRes, &res_full[buf], smO + buf * Cfg::kBufBytes, pre.col0 + pre.c * 32, pre.w0, pre.h0, pre.img0);
         } else {
           mbar_arrive(&res_full[buf]);
         }
-        ++pre_k;
-        if (++pre_c == chunks_of(pre_t)) pre_c = 0, pre_t += n_clusters;
+        advance(pre);
       };
-      for (int i = 0; i < Cfg::kAhead && pre_t < total; ++i) prepare();
-      while (sto_t < total) {
-        if (pre_t < total) prepare();
-        const int buf = sto_k % NBUF;
-        mbar_wait(&out_ready[buf], (sto_k / NBUF) & 1);
-        int col0, w0, h0, img0;
-        if (coords(sto_t, sto_c, col0, w0, h0, img0))
-          tma_store_4d(&tmOut, smO + buf * Cfg::kBufBytes, col0, w0, h0, img0);
+      for (int i = 0; i < Cfg::kAhead && pre.t < total; ++i) prepare();
+      while (sto.t < total) {
+        if (pre.t < total) prepare();
+        const int buf = sto.k % NBUF;
+        mbar_wait(&out_ready[buf], (sto.k / NBUF) & 1);
+        if (sto.real) tma_store_4d(&tmOut, smO + buf * Cfg::kBufBytes, sto.col0 + sto.c * 32, sto.w0, sto.h0, sto.img0);
         bulk_commit_group();  // one group per chunk (empty for the phantom half of an odd pair) keeps the wait counts exact
-        ++sto_k;
-        if (++sto_c == chunks_of(sto_t)) sto_c = 0, sto_t += n_clusters;
+        advance(sto);
       }
       MDB_TRACE3(4);
       bulk_wait_group_all();
