@@ -378,7 +378,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncwarp();
   } else {
     // =========================== epilogue (warps 3 .. 3 + 4 G) ===========================
-    // G groups of four warps (one per TMEM lane quarter); group g owns the 32-column chunks c with c % G == g.  All
+    // G groups of four warps (one per TMEM lane quarter); the 32-column chunks go round-robin to the groups.  All
     // arithmetic on fp32 PAIRS (FFMA2 / FADD2 / FMUL2): out = A_row * acc + (B_row * colsum_n + bias_n) [+ residual] with
     // A_row = rstd * scale, B_row = -mean * rstd * scale (folded LayerNorm) or A_row = scale, B_row = 0.
     constexpr int G = Cfg::kEpiGroups;
@@ -487,7 +487,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
 
       for (int c = 0; c < nch; ++c, ++gk) {
-        if ((c % G) != eg) continue;
+        if ((gk % G) != eg) continue;  // round-robin over the running chunk number: balanced even when a tile has 5 chunks
         const int buf = gk % NBUF;
         const uint32_t srow = my_row + buf * Cfg::kBufBytes;
         if (!geglu) {
