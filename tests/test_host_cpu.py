@@ -159,7 +159,7 @@ def test_unsupported_configurations_raise_like_the_reference_would():
     """Bad / unbuilt configurations are Python exceptions at construction or call time, never a silent different result
     (errors = ValueError for bad config, unet_2d_condition_multiview.py:413-416)."""
     from magicdrive_b200 import arch, models
-    from magicdrive_b200.dist import ViewShard
+    from magicdrive_b200.dist import ShardPlan
     from magicdrive_b200.pipeline import BEVControlNetDenoiser, UniPCSchedule
     ucfg, ccfg = tiny_configs()
     with pytest.raises(ValueError):
@@ -169,7 +169,7 @@ def test_unsupported_configurations_raise_like_the_reference_would():
     with pytest.raises(ValueError):
         models.AutoencoderKL(act_fn="gelu")
     with pytest.raises(ValueError):
-        ViewShard(0, 4, 6)  # 6 cameras do not split over 4 ranks
+        ShardPlan(0, 7, 6, False, [arch.DEFAULT_NEIGHBORS[i] for i in range(6)])  # 6 cameras do not spread over 7 ranks
     with pytest.raises(ValueError):
         UniPCSchedule(solver_order=3)
     un, cn = models.UNet2DConditionModelMultiview(**asdict(ucfg)), models.BEVControlNetModel(**asdict(ccfg))
