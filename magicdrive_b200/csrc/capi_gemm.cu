@@ -257,13 +257,12 @@ int launch3(const Plan3& pl, const CUtensorMap& tA0, const CUtensorMap& tA1, con
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  add_pdl_attr(cfg, attr, 1);
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN, CTAS>, tA0, tA1, tB, tO, tR, gp);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MDB_ERR_CUDA, "gemm_pair_kernel<%d,%d> launch: %s", BN, CTAS, cudaGetErrorString(e));

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __re
                                                        __nv_bfloat16* __restrict__ out, int ldo, uint32_t inv_pp) {
   constexpr int T = 256;
   mdb::pdl_wait();
+  mdb::pdl_launch_dependents();
   extern __shared__ uint32_t slab[];  // [units] bf16x2 (CACHED only)
   __shared__ float red[T / 32];
   __shared__ float bcast;
@@ -221,6 +222,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ out, int ldo) {
   mdb::pdl_wait();
+  mdb::pdl_launch_dependents();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;

@@ -45,13 +45,26 @@ inline EncodeTiledFn get_encode() {
 namespace mdb {
 // Programmatic dependent launch: the kernel may start while its stream predecessor drains; every kernel launched
 // this way executes griddepcontrol.wait before touching global memory (see pdl_wait() in ptx.cuh / kernels).
+#ifndef MDB_PDL_DEFAULT
+#define MDB_PDL_DEFAULT 0
+#endif
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("MDB_PDL");  // opt-in: measured slower than plain stream order on this workload
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("MDB_PDL");  // MDB_PDL=0|1 overrides the default
+    v = e ? ((e[0] == '1') ? 1 : 0) : MDB_PDL_DEFAULT;
   }
   return v == 1;
+}
+// append the PDL attribute to a launch that already carries `n_attrs` attributes (attrs must have room for one more)
+inline void add_pdl_attr(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, unsigned n_attrs) {
+  if (pdl_enabled()) {
+    attrs[n_attrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n_attrs].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attrs;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = n_attrs;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

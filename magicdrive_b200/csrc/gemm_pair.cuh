@@ -40,7 +40,7 @@ struct GemmParams3 {
 };
 
 #ifndef MDB_EPI_GROUPS
-#define MDB_EPI_GROUPS 4
+#define MDB_EPI_GROUPS 2
 #endif
 
 // ---- fp32 pairs in 64-bit registers: FFMA2 / FADD2 / FMUL2 (sm_100) halve the epilogue's instruction count
@@ -229,6 +229,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the predecessor's tail; from here on its results are complete and visible.  The
+  // dependent grid may be scheduled as soon as every CTA of this one holds its shared memory and TMEM.
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x == 0) MDB_TRACE3(1);
 
   if (warp == 0) {

@@ -75,6 +75,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int sp
                                        int rowbias_ld, const __nv_bfloat16* __restrict__ residual, int ldr,
                                        void* __restrict__ out, int ldo, int out_is_f32, float out_scale) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (idx >= pixels * n_out) return;
   const long long pix = idx / n_out;

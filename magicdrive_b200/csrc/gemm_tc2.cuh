@@ -83,6 +83,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the predecessor's tail; from here on
   // we read its outputs / overwrite buffers it may still be reading
   pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -191,7 +192,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_launch_dependents();  // last tile of this CTA: let the next grid stage
       if (warp == 2 && lane == 0 && it == 0) MDB_TRACE(7);
       const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
