@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "../../include/magicdrive_b200.h"
@@ -204,8 +205,14 @@ bool pair_supported(const mdb_gemm_desc* d, const Plan& box) {
   const int out_cols = d->epi_mode == 1 ? d->n_out / 2 : d->n_out;
   if (out_cols % 32 || d->n_out % 32) return false;
   if (d->rowbias && d->rowbias_ld != 0 && box.bn != 1) return false;
+  // the epilogue fetches bias / per-image shift / folded-LayerNorm column sums with warp-uniform 16-byte loads
+  auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+  if (misaligned(d->bias) || misaligned(d->rowbias) || misaligned(d->ln_colsum) || (d->rowbias && d->rowbias_ld % 4)) return false;
   return true;
 }
+
+// ceil(2^32 / d): x / d == umulhi(x, magic) whenever x * d < 2^32
+inline uint32_t div_magic(int d) { return static_cast<uint32_t>((0x100000000ULL + static_cast<uint32_t>(d) - 1) / static_cast<uint32_t>(d)); }
 
 void make_plan3(const mdb_gemm_desc* d, int ctas, Plan3* pl) {
   Plan box;
@@ -369,6 +376,13 @@ extern "C" int mdb_gemm_conv(const mdb_gemm_desc* d, void* stream) {
     g3.ln_stats = d->ln_stats, g3.ln_parts = d->ln_parts, g3.ln_eps = d->ln_eps, g3.ln_colsum = d->ln_colsum;
     g3.ln_inv_c = 1.0f / (float)(d->c0 + d->c1);
     g3.stats_out = d->stats_out;
+    {
+      const long long total_tiles = (long long)p3.m_groups * p3.n_tiles + num_sms();  // the epilogue also locates one tile past the end
+      const long long dmax = std::max(p3.m_groups, std::max(p3.tiles_w, p3.tiles_h));
+      if (total_tiles * dmax >= (1LL << 32) || (long long)(p3.m_groups * p3.ctas + 1) * dmax >= (1LL << 32))
+        return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: tile grid too large for the 32-bit tile decomposition");
+      g3.mg_magic = div_magic(p3.m_groups), g3.tw_magic = div_magic(p3.tiles_w), g3.th_magic = div_magic(p3.tiles_h);
+    }
     return kernel == 2 ? launch3_bn<2>(p3, tA0, tA1, tB, tO, tR, g3, st) : launch3_bn<1>(p3, tA0, tA1, tB, tO, tR, g3, st);
   }
 

@@ -1,12 +1,17 @@
 // GroupNorm(+SiLU) over NHWC (optionally over a two-source channel concat) and LayerNorm.  HBM-bound kernels:
 // 16-byte vector loads along the contiguous channel axis, fp32 statistics, warp-shuffle / smem reductions.
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
 #include "../../include/magicdrive_b200.h"
 #include "common_host.h"
+#include "ptx_cluster.cuh"
+
+// images of at least this many bytes take the pixel-major cluster GroupNorm (MDB_GN_ROWS unset)
+#ifndef MDB_GN_ROWS_MIN_BYTES
+#define MDB_GN_ROWS_MIN_BYTES (1LL << 62)
+#endif
 
 namespace {
 
@@ -276,38 +281,63 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 }
 
 
-// ---- GroupNorm, pixel-major on a cooperative grid (MDB_GN_GRID=1).  Every image is split into contiguous pixel runs, one per
-// CTA (all CTAs co-resident: cooperative launch, grid <= SM count).  A CTA pulls its run into shared memory ONCE with coalesced
-// 16-byte loads, computes per-group (count, mean, M2) of the run exactly (two passes over shared memory), publishes them,
-// and after ONE grid barrier combines the runs of its image (Chan's parallel variance: no E[x^2] - mean^2 cancellation),
-// normalises its run from shared memory (+ affine, + SiLU) and stores it with coalesced 16-byte stores.  One global read and
-// one global write per element, both fully coalesced; gn_fused_kernel reads 20..80-byte channel slices per pixel instead.
+// ---- GroupNorm, pixel-major on a thread-block cluster per image (MDB_GN_ROWS=1 forces it, =0 disables it).  The image's
+// pixels are split into contiguous runs, one per CTA of the cluster.  A CTA pulls its run into shared memory ONCE with
+// one bulk-async copy per pixel row and source (cp.async.bulk, no registers, every byte in flight at once: the per-thread
+// 16-byte-load loop of the first cluster kernel was latency-bound at ~0.8 TB/s), computes per-group (mean, M2) of the run
+// exactly (two passes over shared memory), publishes them in its own shared memory, and after ONE cluster barrier combines
+// the runs of the image through distributed shared memory (Chan's parallel variance: no E[x^2] - mean^2 cancellation),
+// normalises its run from shared memory (+ affine, + SiLU) and stores it with coalesced 16-byte stores.  One global read
+// and one global write per element, both in full rows; gn_fused_kernel reads 20..80-byte channel slices per pixel instead.
 // blockDim = vpp * R (vpp = 16-byte vectors per pixel), thread = (pixel lane r, channel vector cv): a thread's 8 channels,
 // their groups, gamma and beta are fixed for the whole kernel.
-__global__ void gn_grid_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0, const __nv_bfloat16* __restrict__ x1,
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
+  return v;
+}
+__global__ void gn_rows_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int ld0, const __nv_bfloat16* __restrict__ x1,
                                int c1, int ld1, int hw, int groups, float eps, const float* __restrict__ gamma,
                                const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ out, int ldo, int vpp, int R,
-                               int ctas_per_img, int pix_per_cta, float* __restrict__ part /* [grid][groups][2] */) {
-  namespace cg = cooperative_groups;
-  extern __shared__ uint4 gslab[];  // [pix_per_cta][vpp] then float red[R][ctot]
+                               int ctas_per_img, int pix_per_cta) {
+  using namespace mdb;
+  extern __shared__ __align__(128) uint4 gslab[];  // [pix_per_cta][vpp] then float red[R][ctot]
   const int ctot = c0 + c1, cpg = ctot / groups;
   float* red = reinterpret_cast<float*>(gslab + static_cast<size_t>(pix_per_cta) * vpp);  // [R][ctot]
-  __shared__ float g_a[128], g_b[128];  // per group: local mean / M2, later mean / rstd
-  const int img = blockIdx.x / ctas_per_img, run = blockIdx.x % ctas_per_img;
+  __shared__ float g_a[128], g_b[128];  // per group: mean / rstd of the image
+  __shared__ float part[256];           // per group: (mean, M2) of this CTA's run -- read by the cluster peers
+  __shared__ __align__(8) uint64_t full_bar;
+  const int img = blockIdx.x / ctas_per_img, run = blockIdx.x % ctas_per_img;  // run == %cluster_ctarank (1-D clusters)
   const int p_begin = min(hw, run * pix_per_cta), p_end = min(hw, p_begin + pix_per_cta);
   const int npix = p_end - p_begin;
   const int cv = threadIdx.x % vpp, r0 = threadIdx.x / vpp;
   const int ch = cv * 8;
   const long long pix0 = static_cast<long long>(img) * hw + p_begin;
-  const __nv_bfloat16* src = (ch < c0) ? x0 + pix0 * ld0 + ch : x1 + pix0 * ld1 + (ch - c0);
-  const int lds = (ch < c0) ? ld0 : ld1;
-  // ---- one coalesced read of the run, kept in shared memory; per-thread channel sums on the way
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&full_bar, static_cast<uint32_t>(npix) * ctot * 2);
+  }
+  __syncthreads();
+  pdl_wait();  // everything above overlapped the producer's tail
+  pdl_launch_dependents();
+  // ---- one bulk copy per pixel row and source; all complete on full_bar
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const uint32_t dst = smem_u32(gslab) + static_cast<uint32_t>(p) * ctot * 2;
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(x0 + (pix0 + p) * ld0), "r"(c0 * 2), "r"(smem_u32(&full_bar))
+                 : "memory");
+    if (c1 > 0)
+      asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + c0 * 2),
+                   "l"(x1 + (pix0 + p) * ld1), "r"(c1 * 2), "r"(smem_u32(&full_bar))
+                   : "memory");
+  }
+  mbar_wait(&full_bar, 0);
+  // ---- per-channel sums of the run -> per-group local mean
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int p = r0; p < npix; p += R) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * lds));
-    gslab[p * vpp + cv] = u;
     float f[8];
-    unpack8(u, f);
+    unpack8(gslab[p * vpp + cv], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += f[e];
   }
@@ -324,13 +354,13 @@ __global__ void gn_grid_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f;
     for (int c = 0; c < cpg; ++c) s += red[g * cpg + c];
-    g_a[g] = npix > 0 ? s / cnt_local : 0.f;  // local mean
+    part[2 * g] = npix > 0 ? s / cnt_local : 0.f;  // local mean
   }
   __syncthreads();
   // ---- local M2 around the local mean (second pass over shared memory)
   float lm[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) lm[e] = g_a[(ch + e) / cpg], acc[e] = 0.f;
+  for (int e = 0; e < 8; ++e) lm[e] = part[2 * ((ch + e) / cpg)], acc[e] = 0.f;
   for (int p = r0; p < npix; p += R) {
     float f[8];
     unpack8(gslab[p * vpp + cv], f);
@@ -349,33 +379,40 @@ __global__ void gn_grid_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
     red[c] = s;
   }
   __syncthreads();
-  float* mine = part + static_cast<size_t>(blockIdx.x) * groups * 2;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f;
     for (int c = 0; c < cpg; ++c) s += red[g * cpg + c];
-    mine[2 * g] = g_a[g];
-    mine[2 * g + 1] = s;
+    part[2 * g + 1] = s;
   }
-  __threadfence();
-  cg::this_grid().sync();  // every run's (mean, M2) is published
-  // ---- combine the runs of this image (Chan et al.): mean = sum n_i m_i / N, M2 = sum M2_i + sum n_i (m_i - mean)^2
+  // ---- every run's (mean, M2) is published: combine the runs of this image (Chan et al.):
+  //      mean = sum n_i m_i / N,  M2 = sum M2_i + sum n_i (m_i - mean)^2
+  if (ctas_per_img > 1) cluster_sync_all(); else __syncthreads();
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    const float* base = part + static_cast<size_t>(img) * ctas_per_img * groups * 2;
     float wsum = 0.f;
     for (int r = 0; r < ctas_per_img; ++r) {
       const int nb = min(hw, r * pix_per_cta), ne = min(hw, nb + pix_per_cta);
-      wsum += static_cast<float>(ne - nb) * __ldcg(base + (r * groups + g) * 2);
+      const float m = (ctas_per_img > 1) ? ld_dsmem_f32(mapa_u32(smem_u32(&part[2 * g]), r)) : part[2 * g];
+      wsum += static_cast<float>(ne - nb) * m;
     }
     const float mean = wsum / static_cast<float>(hw);
     float m2 = 0.f;
     for (int r = 0; r < ctas_per_img; ++r) {
       const int nb = min(hw, r * pix_per_cta), ne = min(hw, nb + pix_per_cta);
-      const float d = __ldcg(base + (r * groups + g) * 2) - mean;
-      m2 += __ldcg(base + (r * groups + g) * 2 + 1) + static_cast<float>(ne - nb) * static_cast<float>(cpg) * d * d;
+      float m, q;
+      if (ctas_per_img > 1) {
+        const uint32_t a = mapa_u32(smem_u32(&part[2 * g]), r);
+        m = ld_dsmem_f32(a), q = ld_dsmem_f32(a + 4);
+      } else {
+        m = part[2 * g], q = part[2 * g + 1];
+      }
+      const float d = m - mean;
+      m2 += q + static_cast<float>(ne - nb) * static_cast<float>(cpg) * d * d;
     }
     g_a[g] = mean;
     g_b[g] = rsqrtf(m2 / (static_cast<float>(hw) * static_cast<float>(cpg)) + eps);
   }
+  // peers may still be reading this CTA's `part`: arrive now, wait before exit
+  if (ctas_per_img > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   __syncthreads();
   // ---- normalise + affine (+SiLU) from shared memory, coalesced 16-byte stores
   float sa[8], sb[8];
@@ -397,6 +434,7 @@ __global__ void gn_grid_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
     }
     *reinterpret_cast<uint4*>(dst + static_cast<long long>(p) * ldo) = pack8(f);
   }
+  if (ctas_per_img > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace
@@ -413,44 +451,46 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
   if (c1 > 0 && !x1) return set_error(MDB_ERR_INVALID, "mdb_groupnorm: c1>0 but x1 null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
-    // cooperative pixel-major kernel (opt-in while it is being measured: MDB_GN_GRID=1)
-    static int use_grid = -1, sms = 0;
-    if (use_grid < 0) {
-      const char* e = getenv("MDB_GN_GRID");
-      use_grid = (e && e[0] == '1') ? 1 : 0;
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
+    // pixel-major cluster kernel: the default wherever an image is large enough that gn_fused_kernel's channel-slice reads
+    // cost more than the cluster barrier (measured crossover, profiles/); MDB_GN_ROWS=1 forces it, =0 disables it
+    const char* env = getenv("MDB_GN_ROWS");  // read per call: tests flip it inside one process
+    const int mode = env ? ((env[0] == '1') ? 1 : 0) : -1;
     const int vpp = ctot / 8;
-    if (use_grid && groups <= 128 && n_img <= sms && vpp <= 512) {
+    const long long img_bytes = static_cast<long long>(hw) * ctot * 2;
+    const bool want = mode == 1 || (mode == -1 && img_bytes >= MDB_GN_ROWS_MIN_BYTES);
+    if (want && groups <= 128 && vpp <= 1024 && ld0 % 8 == 0 && (c1 == 0 || ld1 % 8 == 0)) {
       int R = 512 / vpp;
       if (R < 1) R = 1;
-      int cpi = sms / n_img;                     // CTAs per image
-      if (cpi > (hw + R - 1) / R) cpi = (hw + R - 1) / R;
-      if (cpi < 1) cpi = 1;
-      const int ppc = (hw + cpi - 1) / cpi;
-      cpi = (hw + ppc - 1) / ppc;                // no empty runs
-      const size_t smem = static_cast<size_t>(ppc) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
-      if (smem <= 200 * 1024) {
+      // largest portable cluster (<= 8 CTAs per image: more SMs pull on the image) whose runs still give every pixel lane two
+      // pixels and fit in shared memory
+      constexpr size_t kMaxSmem = 200 * 1024;
+      int cpi = 0, ppc = 0;
+      size_t smem = 0;
+      for (int cand = 8; cand >= 1; cand /= 2) {
+        const int pp = (hw + cand - 1) / cand;
+        const size_t need = static_cast<size_t>(pp) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
+        if (need <= kMaxSmem && (pp >= 2 * R || cand == 1) && (cand - 1) * pp < hw) {
+          cpi = cand, ppc = pp, smem = need;
+          break;
+        }
+      }
+      if (cpi > 0) {
         static bool attr = false;
         if (!attr) {
-          cudaFuncSetAttribute(gn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(gn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
           attr = true;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cpi * n_img), cfg.blockDim = dim3(vpp * R), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-        cudaLaunchAttribute la[1];
-        la[0].id = cudaLaunchAttributeCooperative;
-        la[0].val.cooperative = 1;
-        cfg.attrs = la, cfg.numAttrs = 1;
-        // the per-run partials live at the tail of the caller's scratch (n_img * groups * 2 floats are reserved for the
-        // two-kernel path; the grid kernel needs grid * groups * 2 <= sms * groups * 2: the caller sizes stats_ws for that)
-        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_grid_kernel, static_cast<const __nv_bfloat16*>(x0), c0, ld0,
+        cudaLaunchAttribute la[2];
+        la[0].id = cudaLaunchAttributeClusterDimension;
+        la[0].val.clusterDim.x = cpi, la[0].val.clusterDim.y = 1, la[0].val.clusterDim.z = 1;
+        add_pdl_attr(cfg, la, 1);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_rows_kernel, static_cast<const __nv_bfloat16*>(x0), c0, ld0,
                                             static_cast<const __nv_bfloat16*>(x1), c1, ld1, hw, groups, eps, gamma, beta, silu,
-                                            static_cast<__nv_bfloat16*>(out), ldo, vpp, R, cpi, ppc, stats_ws);
-        if (le != cudaSuccess) return set_error(MDB_ERR_CUDA, "gn_grid_kernel launch: %s", cudaGetErrorString(le));
-        MDB_CHECK_LAUNCH("gn_grid_kernel");
+                                            static_cast<__nv_bfloat16*>(out), ldo, vpp, R, cpi, ppc);
+        if (le != cudaSuccess) return set_error(MDB_ERR_CUDA, "gn_rows_kernel launch: %s", cudaGetErrorString(le));
+        MDB_CHECK_LAUNCH("gn_rows_kernel");
         return MDB_OK;
       }
     }

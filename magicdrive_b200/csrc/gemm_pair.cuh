@@ -37,6 +37,8 @@ struct GemmParams3 {
   const float* ln_colsum;  // [n_out] sum_k W'[n, k]
   // row statistics of this GEMM's bf16 output (producer side)
   float* stats_out;        // [pixels][n_tiles * kEpiGroups][2] or nullptr
+  // ceil(2^32 / d) for d = m_groups, tiles_w, tiles_h: x / d = umulhi(x, magic) for x * d < 2^32 (host check)
+  uint32_t mg_magic, tw_magic, th_magic;
 };
 
 #ifndef MDB_EPI_GROUPS
@@ -389,7 +391,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int NEPI = 128 * G;
     const int q = warp & 3;
     const int eg = (warp - 3) >> 2;
-    const int etid = threadIdx.x - 96;
     const int row = q * 32 + lane;
     const int box_hw = p.bh * p.bw;
     const int li = row / box_hw;
@@ -397,77 +398,76 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int lh = rem / p.bw;
     const int lw = rem - lh * p.bw;
     const uint32_t my_row = smem_u32(smO) + row * 64;  // this thread's 64-byte row inside a staging box (shared-space address)
-    const uint32_t smC_u32 = smem_u32(smC);
     const int swz = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk j sits at j ^ swz
     const bool has_ln = pp.ln_stats != nullptr;
     const float scale = p.out_scale;
-    // per-tile constants (bias + per-image shift, folded-LayerNorm column sums) are fetched one tile ahead
-    auto tile_coords = [&](int t, int& nt, int& mt, int& tn, int& th, int& tw) {
-      const int mg = t % pp.m_groups;
-      nt = t / pp.m_groups;
-      mt = mg * CTAS + static_cast<int>(rank);
-      tw = mt % p.tiles_w;
-      th = (mt / p.tiles_w) % p.tiles_h;
-      tn = mt / (p.tiles_w * p.tiles_h);
+    // Where this thread's accumulator row lands for tile t: one decomposition per tile (multiply-high by host-computed
+    // reciprocals, no integer division), carried from the prefetch of the previous iteration.
+    struct TileRow {
+      int nt;        // N tile
+      int img_tile;  // image of the tile (per-image shift: one image per tile, host check)
+      int pix;       // output pixel of this row
+      bool ok;       // row is a real output pixel
     };
-    auto fetch_consts = [&](int t, float& b, float& cs) {
-      b = 0.f, cs = 0.f;
-      if (etid < BLOCK_N && t < total) {
-        int nt, mt, tn, th, tw;
-        tile_coords(t, nt, mt, tn, th, tw);
-        const int n = nt * BLOCK_N + etid;
-        if (n < p.n_out) {
-          const int img_tile = min(tn * p.bn, p.n_img - 1);  // one image per tile whenever a per-image shift is used (host check)
-          if (p.bias) b = __ldg(p.bias + n);
-          if (p.rowbias) b += __ldg(p.rowbias + static_cast<long long>(img_tile) * p.rowbias_ld + n);
-          b *= scale;
-          if (has_ln) cs = __ldg(pp.ln_colsum + n);
-        }
-      }
-    };
-    auto row_pix = [&](int t, bool& ok) {
-      int nt, mt, tn, th, tw;
-      tile_coords(t, nt, mt, tn, th, tw);
+    // x / d (x * d < 2^32, host check): ceil(2^32 / d) does not fit 32 bits for d == 1, which is taken apart (uniform select)
+    auto fdiv = [](int x, uint32_t magic, int d) { return d == 1 ? x : static_cast<int>(__umulhi(static_cast<uint32_t>(x), magic)); };
+    auto locate = [&](int t) {
+      TileRow r;
+      r.nt = fdiv(t, pp.mg_magic, pp.m_groups);
+      const int mt = (t - r.nt * pp.m_groups) * CTAS + static_cast<int>(rank);
+      const int a = fdiv(mt, pp.tw_magic, p.tiles_w);
+      const int tw = mt - a * p.tiles_w;
+      const int tn = fdiv(a, pp.th_magic, p.tiles_h);
+      const int th = a - tn * p.tiles_h;
       const int img = tn * p.bn + li, oh = th * p.bh + lh, ow = tw * p.bw + lw;
-      ok = (t < total) && (mt < pp.m_tiles) && (li < p.bn) && (img < p.n_img) && (oh < p.h_out) && (ow < p.w_out);
-      return (static_cast<long long>(img) * p.h_out + oh) * p.w_out + ow;
+      r.ok = (t < total) && (mt < pp.m_tiles) && (li < p.bn) && (img < p.n_img) && (oh < p.h_out) && (ow < p.w_out);
+      r.pix = (img * p.h_out + oh) * p.w_out + ow;
+      r.img_tile = min(tn * p.bn, p.n_img - 1);
+      return r;
     };
-    constexpr int PF = 4;  // LayerNorm row-statistics partials fetched one tile ahead (the rest, if any, at use)
+    constexpr int PF = (G <= 2) ? 8 : 4;  // LayerNorm row-statistics partials fetched one tile ahead (the rest, if any, at use)
     float2 pf[PF];
-    auto fetch_stats = [&](int t) {
+    auto fetch_stats = [&](const TileRow& r) {
 #pragma unroll
       for (int j = 0; j < PF; ++j) pf[j] = make_float2(0.f, 0.f);
-      bool ok;
-      const long long pix = row_pix(t, ok);
-      if (has_ln && ok) {
-        const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + pix * pp.ln_parts;
+      if (has_ln && r.ok) {
+        const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + static_cast<long long>(r.pix) * pp.ln_parts;
 #pragma unroll
         for (int j = 0; j < PF; ++j)
           if (j < pp.ln_parts) pf[j] = __ldg(sp + j);
       }
     };
-    float nb, ncs;
-    fetch_consts(cluster_id, nb, ncs);
-    fetch_stats(cluster_id);
-    if (etid < BLOCK_N) smC[etid] = nb, smC[256 + etid] = ncs;
+    // bias (+ per-image shift) and folded-LayerNorm column sums of four consecutive columns: warp-uniform 16-byte loads
+    // straight from global memory (L1 hits after the first warp): no shared staging, no CTA-wide barrier per tile
+    auto col_consts = [&](const float* rowb, int n, unsigned long long B2, unsigned long long& t0, unsigned long long& t1) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      if (rowb) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(rowb + n));
+        b.x += r.x, b.y += r.y, b.z += r.z, b.w += r.w;
+      }
+      if (scale != 1.f) b.x *= scale, b.y *= scale, b.z *= scale, b.w *= scale;
+      t0 = pk2(b.x, b.y), t1 = pk2(b.z, b.w);
+      if (has_ln) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(pp.ln_colsum + n));
+        t0 = fma2(B2, pk2(cs.x, cs.y), t0), t1 = fma2(B2, pk2(cs.z, cs.w), t1);
+      }
+    };
+    TileRow cur = locate(cluster_id);
+    fetch_stats(cur);
     int it = 0;
     int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
     for (int t = cluster_id; t < total; t += n_clusters, ++it) {
-      int nt, mt, tn, th, tw;
-      tile_coords(t, nt, mt, tn, th, tw);
-      bool row_ok;
-      const long long pix = row_pix(t, row_ok);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const uint32_t cst = smC_u32 + as * 2048;  // [bias + shift | colsum] fp32 x 256 each
       // this tile's row scalars from the prefetched statistics
       float rowA = scale, rowB = 0.f;
       if (has_ln) {
         float s = 0.f, ss = 0.f;
 #pragma unroll
         for (int j = 0; j < PF; ++j) s += pf[j].x, ss += pf[j].y;
-        if (row_ok) {
-          const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + pix * pp.ln_parts;
+        if (cur.ok) {
+          const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + static_cast<long long>(cur.pix) * pp.ln_parts;
           for (int j = PF; j < pp.ln_parts; ++j) {
             const float2 v = __ldg(sp + j);
             s += v.x, ss += v.y;
@@ -478,17 +478,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         rowA = rstd * scale;
         rowB = -mean * rowA;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // constants of this tile visible; everyone left the previous tile
-      // next tile's constants / statistics: loads in flight while this tile is processed
-      fetch_consts(t + n_clusters, nb, ncs);
-      fetch_stats(t + n_clusters);
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
-      const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      const int left = (pp.out_cols - nt * out_per_tile) / 32;
+      // next tile's position / statistics: loads in flight while this tile is processed
+      const TileRow nxt = locate(t + n_clusters);
+      fetch_stats(nxt);
+      const int nbase = cur.nt * BLOCK_N;
+      const float* rowb = p.rowbias ? p.rowbias + static_cast<long long>(cur.img_tile) * p.rowbias_ld : nullptr;
+      const int left = (pp.out_cols - cur.nt * out_per_tile) / 32;
       const int nch = left < ch_tile ? left : ch_tile;
       const unsigned long long A2 = pk2(rowA, rowA), B2 = pk2(rowB, rowB);
       unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
       for (int c = 0; c < nch; ++c, ++gk) {
         if ((gk % G) != eg) continue;  // round-robin over the running chunk number: balanced even when a tile has 5 chunks
@@ -496,31 +497,32 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t srow = my_row + buf * Cfg::kBufBytes;
         if (!geglu) {
           uint32_t v[32];
-          tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while we wait for the staging box
+          tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while the constants are fetched and the staging box is awaited
+          unsigned long long pre[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) col_consts(rowb, nbase + c * 32 + 4 * j, B2, pre[2 * j], pre[2 * j + 1]);
           mbar_wait(&res_full[buf], (gk / NBUF) & 1);
-          const uint32_t cb = cst + c * 128;
+          uint4 r[4];
+          if (pp.use_res_tma) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = lds_u4(srow + ((j ^ swz) << 4));
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b0 = lds_f4(cb + 32 * j), b1 = lds_f4(cb + 32 * j + 16);
-            unsigned long long t0 = pk2(b0.x, b0.y), t1 = pk2(b0.z, b0.w), t2 = pk2(b1.x, b1.y), t3 = pk2(b1.z, b1.w);
-            if (has_ln) {
-              const float4 s0 = lds_f4(cb + 1024 + 32 * j), s1 = lds_f4(cb + 1024 + 32 * j + 16);
-              t0 = fma2(B2, pk2(s0.x, s0.y), t0), t1 = fma2(B2, pk2(s0.z, s0.w), t1);
-              t2 = fma2(B2, pk2(s1.x, s1.y), t2), t3 = fma2(B2, pk2(s1.z, s1.w), t3);
-            }
-            unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), t0), o1 = fma2(A2, pk2u(v[8 * j + 2], v[8 * j + 3]), t1);
-            unsigned long long o2 = fma2(A2, pk2u(v[8 * j + 4], v[8 * j + 5]), t2), o3 = fma2(A2, pk2u(v[8 * j + 6], v[8 * j + 7]), t3);
-            const uint32_t slot = srow + ((j ^ swz) << 4);
+            unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), pre[4 * j]);
+            unsigned long long o1 = fma2(A2, pk2u(v[8 * j + 2], v[8 * j + 3]), pre[4 * j + 1]);
+            unsigned long long o2 = fma2(A2, pk2u(v[8 * j + 4], v[8 * j + 5]), pre[4 * j + 2]);
+            unsigned long long o3 = fma2(A2, pk2u(v[8 * j + 6], v[8 * j + 7]), pre[4 * j + 3]);
             if (pp.use_res_tma) {
-              const uint4 r = lds_u4(slot);
-              o0 = add2(o0, bf2_to_f2(r.x)), o1 = add2(o1, bf2_to_f2(r.y)), o2 = add2(o2, bf2_to_f2(r.z)), o3 = add2(o3, bf2_to_f2(r.w));
+              o0 = add2(o0, bf2_to_f2(r[j].x)), o1 = add2(o1, bf2_to_f2(r[j].y));
+              o2 = add2(o2, bf2_to_f2(r[j].z)), o3 = add2(o3, bf2_to_f2(r[j].w));
             }
             if (pp.stats_out) {
               st_s2 = add2(add2(st_s2, add2(o0, o1)), add2(o2, o3));
               st_ss2 = fma2(o0, o0, fma2(o1, o1, fma2(o2, o2, fma2(o3, o3, st_ss2))));
             }
-            sts_u4(slot, make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3)));
+            sts_u4(srow + ((j ^ swz) << 4), make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3)));
           }
         } else {
           constexpr int HALF = BLOCK_N / 2;
@@ -530,24 +532,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t v[16], g[16];
             tmem_ld_32x16(lane_addr + c * 32 + hh * 16, v);
             tmem_ld_32x16(lane_addr + HALF + c * 32 + hh * 16, g);
-            const uint32_t cv = cst + (c * 32 + hh * 16) * 4;
-            const uint32_t cg = cst + (HALF + c * 32 + hh * 16) * 4;
+            unsigned long long tv[8], tg[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              col_consts(rowb, nbase + c * 32 + hh * 16 + 4 * j, B2, tv[2 * j], tv[2 * j + 1]);
+              col_consts(rowb, nbase + HALF + c * 32 + hh * 16 + 4 * j, B2, tg[2 * j], tg[2 * j + 1]);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               unsigned long long o[4];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const float4 bv = lds_f4(cv + (2 * j + e) * 16), bg = lds_f4(cg + (2 * j + e) * 16);
-                unsigned long long tv0 = pk2(bv.x, bv.y), tv1 = pk2(bv.z, bv.w), tg0 = pk2(bg.x, bg.y), tg1 = pk2(bg.z, bg.w);
-                if (has_ln) {
-                  const float4 sv = lds_f4(cv + 1024 + (2 * j + e) * 16), sg = lds_f4(cg + 1024 + (2 * j + e) * 16);
-                  tv0 = fma2(B2, pk2(sv.x, sv.y), tv0), tv1 = fma2(B2, pk2(sv.z, sv.w), tv1);
-                  tg0 = fma2(B2, pk2(sg.x, sg.y), tg0), tg1 = fma2(B2, pk2(sg.z, sg.w), tg1);
-                }
                 const int k = 8 * j + 4 * e;
-                const unsigned long long a0 = fma2(A2, pk2u(v[k], v[k + 1]), tv0), a1 = fma2(A2, pk2u(v[k + 2], v[k + 3]), tv1);
-                const unsigned long long g0 = fma2(A2, pk2u(g[k], g[k + 1]), tg0), g1 = fma2(A2, pk2u(g[k + 2], g[k + 3]), tg1);
+                const unsigned long long a0 = fma2(A2, pk2u(v[k], v[k + 1]), tv[k / 2]), a1 = fma2(A2, pk2u(v[k + 2], v[k + 3]), tv[k / 2 + 1]);
+                const unsigned long long g0 = fma2(A2, pk2u(g[k], g[k + 1]), tg[k / 2]), g1 = fma2(A2, pk2u(g[k + 2], g[k + 3]), tg[k / 2 + 1]);
                 o[2 * e] = mul2(a0, gelu_erf2(g0));
                 o[2 * e + 1] = mul2(a1, gelu_erf2(g1));
               }
@@ -559,12 +558,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&out_ready[buf]);
       }
-      if (pp.stats_out && row_ok) {
+      if (pp.stats_out && cur.ok) {
         float s0, s1, q0, q1;
         upk2(st_s2, s0, s1);
         upk2(st_ss2, q0, q1);
         // one slot per (N tile, epilogue group): [pix][n_tiles][G]
-        reinterpret_cast<float2*>(pp.stats_out)[(pix * pp.n_tiles + nt) * G + eg] = make_float2(s0 + s1, q0 + q1);
+        reinterpret_cast<float2*>(pp.stats_out)[(static_cast<long long>(cur.pix) * pp.n_tiles + cur.nt) * G + eg] =
+            make_float2(s0 + s1, q0 + q1);
       }
       // release this accumulator stage to the MMA warp of the leader CTA
       tc_fence_before();
@@ -573,11 +573,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
         else mbar_arrive(&acc_empty[as]);
       }
-      // publish the next tile's constants (buffer of the other accumulator stage: nobody reads it any more, see bar.sync)
-      if (etid < BLOCK_N) {
-        float* nx = smC + (as ^ 1) * 512;
-        nx[etid] = nb, nx[256 + etid] = ncs;
-      }
+      cur = nxt;
       if (warp == 3 && lane == 0 && it == 0) MDB_TRACE3(8);
     }
     if (warp == 3 && lane == 0) MDB_TRACE3(6);

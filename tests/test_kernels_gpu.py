@@ -145,6 +145,37 @@ def test_groupnorm(cuda_lib, c0, c1, hw, n, silu):
     assert _rel(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("c0,c1,hw,n,pad", [(320, 0, 1400, 12, 0), (640, 0, 350, 12, 64), (320, 320, 1400, 3, 0), (640, 320, 350, 2, 8),
+                                             (1280, 1280, 91, 5, 0), (1280, 0, 28, 12, 0), (64, 0, 1400, 2, 0), (320, 0, 37, 3, 0),
+                                             (1280, 640, 350, 2, 0)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm_cluster_rows(cuda_lib, monkeypatch, c0, c1, hw, n, pad, silu):
+    """pixel-major cluster kernel (forced): same fp32 reference, and agreement with the (image, group) kernel; `pad` =
+    extra row stride of the first source (a channel slice of a wider buffer)."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    wide = _bf(torch.randn(n * hw, c0 + pad, device="cuda", generator=g) * 2 + 0.5)
+    xa = wide[:, :c0]
+    xb = _bf(torch.randn(n * hw, c1, device="cuda", generator=g)) if c1 else None
+    c = c0 + c1
+    gamma = torch.randn(c, device="cuda", generator=g)
+    beta = torch.randn(c, device="cuda", generator=g)
+    full = xa if xb is None else torch.cat([xa, xb], 1)
+    ref = F.group_norm(full.float().reshape(n, hw, c).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(n * hw, c)
+    monkeypatch.setenv("MDB_GN_ROWS", "0")
+    base = ops.groupnorm(xa, c0, c0 + pad, n, hw, gamma, beta, 1e-5, silu, x1=xb, c1=c1, ld1=c1)
+    monkeypatch.setenv("MDB_GN_ROWS", "1")
+    out = ops.groupnorm(xa, c0, c0 + pad, n, hw, gamma, beta, 1e-5, silu, x1=xb, c1=c1, ld1=c1)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < 0.06
+    assert _rel(out, ref) < 8e-3
+    assert _rel(out, ref) <= _rel(base, ref) * 1.05 + 1e-5
+    # both kernels round the same fp32 values up to the last bits of mean / rstd: a handful of one-ulp flips at most
+    assert (out != base).float().mean().item() < 2e-3
+
+
 @pytest.mark.parametrize("c", [64, 320, 640, 1280])
 def test_layernorm(cuda_lib, c):
     g = torch.Generator(device="cuda").manual_seed(8)
