@@ -27,6 +27,11 @@ extern "C" {
 #define MDB_ERR_UNSUPPORTED (-3)
 
 const char* mdb_last_error(void);
+
+/* Programmatic dependent launch for the launches that follow (process-wide flag, returns the previous value): the next
+ * kernel's launch latency and prologue overlap the tail of its stream predecessor.  Switch it on only around
+ * single-stream regions (the UNet up path); the environment variable MDB_PDL=0|1 overrides the flag. */
+int mdb_set_pdl(int on);
 int mdb_version(void);
 /* 1 if a CUDA device of compute capability 10.x is usable, else 0 (never raises). */
 int mdb_device_ok(void);

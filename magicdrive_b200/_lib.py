@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "mdb_last_error": (C.c_char_p, []),
+    "mdb_set_pdl": (_i, [_i]),
     "mdb_version": (_i, []),
     "mdb_device_ok": (_i, []),
     "mdb_gemm_conv": (_i, [C.POINTER(GemmDesc), _vp]),

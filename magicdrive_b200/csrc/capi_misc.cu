@@ -12,6 +12,13 @@ char* error_buffer() {
 }  // namespace mdb
 
 extern "C" const char* mdb_last_error(void) { return mdb::error_buffer(); }
+
+extern "C" int mdb_set_pdl(int on) {
+  int& f = mdb::pdl_region_flag();
+  const int old = f;
+  f = on ? 1 : 0;
+  return old;
+}
 extern "C" int mdb_version(void) { return 100; }
 extern "C" int mdb_device_ok(void) {
   int n = 0;

@@ -462,24 +462,49 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
       int R = 512 / vpp;
       if (R < 1) R = 1;
       // largest portable cluster (<= 8 CTAs per image: more SMs pull on the image) whose runs still give every pixel lane two
-      // pixels and fit in shared memory
+      // pixels and fit in shared memory; images too large for 8 CTAs (the 28x50 level's skip concats) take a 16-CTA cluster
+      // (non-portable size: the driver is asked whether one fits a GPC before it is used)
       constexpr size_t kMaxSmem = 200 * 1024;
+      static bool attr = false;
+      static int max16 = -1;  // >0: 16-CTA clusters of this kernel can be co-scheduled
+      if (!attr) {
+        cudaFuncSetAttribute(gn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
+        max16 = (cudaFuncSetAttribute(gn_rows_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) ? 1 : 0;
+        cudaGetLastError();
+        attr = true;
+      }
       int cpi = 0, ppc = 0;
       size_t smem = 0;
+      auto need_for = [&](int cand, int& pp) {
+        pp = (hw + cand - 1) / cand;
+        return static_cast<size_t>(pp) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
+      };
       for (int cand = 8; cand >= 1; cand /= 2) {
-        const int pp = (hw + cand - 1) / cand;
-        const size_t need = static_cast<size_t>(pp) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
-        if (need <= kMaxSmem && (pp >= 2 * R || cand == 1) && (cand - 1) * pp < hw) {
+        int pp;
+        const size_t need = need_for(cand, pp);
+        if (need > kMaxSmem) break;  // smaller clusters need even more
+        if ((pp >= 2 * R || cand == 1) && (cand - 1) * pp < hw) {
           cpi = cand, ppc = pp, smem = need;
           break;
         }
       }
-      if (cpi > 0) {
-        static bool attr = false;
-        if (!attr) {
-          cudaFuncSetAttribute(gn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
-          attr = true;
+      if (cpi == 0 && max16 > 0) {
+        int pp;
+        const size_t need = need_for(16, pp);
+        if (need <= kMaxSmem && 15 * pp < hw) {
+          cudaLaunchConfig_t probe = {};
+          probe.gridDim = dim3(16 * n_img), probe.blockDim = dim3(vpp * R), probe.dynamicSmemBytes = need;
+          cudaLaunchAttribute pa[1];
+          pa[0].id = cudaLaunchAttributeClusterDimension;
+          pa[0].val.clusterDim.x = 16, pa[0].val.clusterDim.y = 1, pa[0].val.clusterDim.z = 1;
+          probe.attrs = pa, probe.numAttrs = 1;
+          int n_clusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&n_clusters, gn_rows_kernel, &probe) == cudaSuccess && n_clusters >= 1)
+            cpi = 16, ppc = pp, smem = need;
+          cudaGetLastError();
         }
+      }
+      if (cpi > 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cpi * n_img), cfg.blockDim = dim3(vpp * R), cfg.dynamicSmemBytes = smem, cfg.stream = st;
         cudaLaunchAttribute la[2];

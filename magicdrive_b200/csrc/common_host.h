@@ -45,16 +45,20 @@ inline EncodeTiledFn get_encode() {
 namespace mdb {
 // Programmatic dependent launch: the kernel may start while its stream predecessor drains; every kernel launched
 // this way executes griddepcontrol.wait before touching global memory (see pdl_wait() in ptx.cuh / kernels).
-#ifndef MDB_PDL_DEFAULT
-#define MDB_PDL_DEFAULT 0
-#endif
+// Who decides: MDB_PDL=0 | 1 in the environment forces it off / on for every launch; otherwise the caller switches it per
+// region with mdb_set_pdl() (off by default).  It pays only where ONE stream is busy: with two concurrent branches the
+// early-scheduled dependents park on SMs the other branch would have filled (measured: whole step 3 % slower).
+inline int& pdl_region_flag() {
+  static int v = 0;
+  return v;
+}
 inline bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDB_PDL");  // MDB_PDL=0|1 overrides the default
-    v = e ? ((e[0] == '1') ? 1 : 0) : MDB_PDL_DEFAULT;
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("MDB_PDL");
+    forced = e ? ((e[0] == '1') ? 1 : 0) : -1;
   }
-  return v == 1;
+  return forced >= 0 ? forced == 1 : pdl_region_flag() == 1;
 }
 // append the PDL attribute to a launch that already carries `n_attrs` attributes (attrs must have room for one more)
 inline void add_pdl_attr(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, unsigned n_attrs) {

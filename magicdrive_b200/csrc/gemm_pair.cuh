@@ -453,7 +453,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         t0 = fma2(B2, pk2(cs.x, cs.y), t0), t1 = fma2(B2, pk2(cs.z, cs.w), t1);
       }
     };
+    // the constants of a tile are pulled into L1 a whole tile ahead (first touch per SM would otherwise cost every chunk an
+    // L2 round trip): lane l of one warp covers columns [32 l, 32 l + 32) = one 128-byte line per array
+    auto prefetch_consts = [&](const TileRow& r, int t) {
+      if (warp != 3 || t >= total) return;
+      const int n = r.nt * BLOCK_N + lane * 32;
+      if (lane * 32 < BLOCK_N && n < p.n_out) {
+        if (p.bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n));
+        if (has_ln) asm volatile("prefetch.global.L1 [%0];" ::"l"(pp.ln_colsum + n));
+        if (p.rowbias) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.rowbias + static_cast<long long>(r.img_tile) * p.rowbias_ld + n));
+      }
+    };
     TileRow cur = locate(cluster_id);
+    prefetch_consts(cur, cluster_id);
     fetch_stats(cur);
     int it = 0;
     int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
@@ -480,6 +492,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       // next tile's position / statistics: loads in flight while this tile is processed
       const TileRow nxt = locate(t + n_clusters);
+      prefetch_consts(nxt, t + n_clusters);
       fetch_stats(nxt);
       const int nbase = cur.nt * BLOCK_N;
       const float* rowb = p.rowbias ? p.rowbias + static_cast<long long>(cur.img_tile) * p.rowbias_ld : nullptr;

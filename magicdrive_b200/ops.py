@@ -5,6 +5,7 @@ torch is plumbing only: it owns device memory and the CUDA stream; every functio
 Feature maps are NHWC bf16 ("channels innermost") everywhere; a token matrix [tokens, C] is the same layout.
 """
 import ctypes as C
+import contextlib
 import os
 from typing import Optional
 
@@ -183,6 +184,18 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, n_img: int, h_in: int, w_in:
               f"geglu={int(geglu)} res={int(residual is not None)}")
     _launches += L.mdb_gemm_conv_launches(C.byref(d))
     return (out, stats) if emit_stats else out
+
+
+@contextlib.contextmanager
+def pdl_region(enabled: bool = True):
+    """Launch the kernels issued inside with programmatic dependent launch (mdb_set_pdl): use around single-stream
+    stretches only -- with two concurrent branches the early-scheduled dependents take SMs from the other branch."""
+    lib = _lib.lib()
+    old = lib.mdb_set_pdl(int(enabled))
+    try:
+        yield
+    finally:
+        lib.mdb_set_pdl(old)
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, ldo=None, geglu=False,

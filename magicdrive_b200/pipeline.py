@@ -14,6 +14,8 @@ the optional VAE decode of the result (`vae=`, output_type "pt" / "np").
 """
 from typing import Dict, Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -150,6 +152,8 @@ class BEVControlNetDenoiser:
             raise ValueError(f"scheduler must be 'ddim' or 'unipc', got {scheduler!r}")
         self.unet, self.controlnet, self.vae = unet, controlnet, vae
         self.overlap_controlnet = overlap_controlnet
+        # programmatic dependent launch on the single-stream UNet up path (A/B switch until measured: MDB_PDL_DECODER=1)
+        self.pdl_decoder = os.environ.get("MDB_PDL_DECODER", "0") == "1"
         self.cfg_streams = cfg_streams
         self.view_shard = view_shard
         unet.set_view_shard(view_shard)
@@ -274,7 +278,9 @@ class BEVControlNetDenoiser:
                                              temb_all=st["c_temb"])
             xe, skips = ue.forward_encoder(x, V, h, w, st["u_temb"], st["u_kv"], st["lc"])
             main.wait_stream(side)
-            eps = ue.forward_decoder(xe, skips, st["u_temb"], st["u_kv"], st["lc"], down, mid)
+            # single stream from here on: the next kernel's launch + prologue may overlap its predecessor's tail
+            with ops.pdl_region(self.pdl_decoder):
+                eps = ue.forward_decoder(xe, skips, st["u_temb"], st["u_kv"], st["lc"], down, mid)
         else:
             down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
                                          temb_all=st.get("c_temb"))
