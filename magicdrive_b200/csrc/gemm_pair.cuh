@@ -184,8 +184,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int out_per_tile = geglu ? BLOCK_N / 2 : BLOCK_N;
   const int ch_tile = geglu ? CH_GLU : CH_LIN;
 
-  // optional per-CTA phase stamps (debug / tools/bench_gemm.py --trace): 16 int64 slots per CTA, globaltimer ns
-  long long* trace = (p.trace != nullptr && blockIdx.x < 160) ? p.trace + blockIdx.x * 16 : nullptr;
+  // optional per-CTA phase stamps (debug / tools/bench_gemm.py --trace): 64 int64 slots per CTA, globaltimer ns; slots 16.. hold
+  // the chunk-level stamps of the first epilogue warp over its first two tiles
+  long long* trace = (p.trace != nullptr && blockIdx.x < 160) ? p.trace + blockIdx.x * 64 : nullptr;  // 64 slots per CTA
 #define MDB_TRACE3(slot)                                                    \
   do {                                                                      \
     if (trace) {                                                            \
@@ -503,6 +504,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      int tslot = (warp == 3 && lane == 0 && it < 2) ? 16 + it * 20 : -1;  // [acc_full | (box ready, acc read, stored, arrived) x <= 4]
+      if (tslot >= 0) {
+        MDB_TRACE3(tslot);
+        ++tslot;
+      }
+      const int tslot_end = tslot + 16;
+#define MDB_TRACE_CHUNK() do { if (tslot >= 0 && tslot < tslot_end) { MDB_TRACE3(tslot); ++tslot; } } while (0)
 
       for (int c = 0; c < nch; ++c, ++gk) {
         if ((gk % G) != eg) continue;  // round-robin over the running chunk number: balanced even when a tile has 5 chunks
@@ -515,12 +523,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) col_consts(rowb, nbase + c * 32 + 4 * j, B2, pre[2 * j], pre[2 * j + 1]);
           mbar_wait(&res_full[buf], (gk / NBUF) & 1);
+          MDB_TRACE_CHUNK();
           uint4 r[4];
           if (pp.use_res_tma) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) r[j] = lds_u4(srow + ((j ^ swz) << 4));
           }
           tmem_ld_wait();
+          MDB_TRACE_CHUNK();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), pre[4 * j]);
@@ -567,10 +577,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
         }
+        if (!geglu) MDB_TRACE_CHUNK();
         fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) mbar_arrive(&out_ready[buf]);
+        if (!geglu) MDB_TRACE_CHUNK();
       }
+#undef MDB_TRACE_CHUNK
       if (pp.stats_out && cur.ok) {
         float s0, s1, q0, q1;
         upk2(st_s2, s0, s1);

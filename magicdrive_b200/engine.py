@@ -559,21 +559,27 @@ class VaeDecoderEngine:
         wk, bk = W.lin(a + ".to_k")
         wv, bv = W.lin(a + ".to_v")
         q = ops.linear(t, wq, bias=bq)
-        k = ops.linear(t, wk, bias=bk)
         lp = (L + 63) // 64 * 64  # keys padded to whole K blocks of the P.V product
         # persistent scratch (no per-call allocation or zero-fill: the decode is captured in a CUDA graph): scores and
         # probabilities [L, lp] per image, V^T [C, lp] whose pad columns stay zero from allocation (P is zero there too)
         key = ("vae_attn", x.n, L, C)
         if key not in W.t:
             dev = q.device
+            # keys live in a buffer with lp - L spare rows so that every image's score GEMM can take lp "keys" (its n_out must
+            # be a multiple of 8): the extra columns are another image's keys or the zero tail, and softmax_rows drops them
             W.t[key] = (torch.empty((x.n, L, lp), dtype=F32, device=dev), torch.zeros((x.n, C, lp), dtype=q.dtype, device=dev),
-                        torch.empty((x.n * L, C), dtype=q.dtype, device=dev))
-        sbuf, vtbuf, o = W.t[key]
+                        torch.empty((x.n * L, C), dtype=q.dtype, device=dev), torch.zeros((x.n * L + lp - L, C), dtype=q.dtype, device=dev),
+                        torch.zeros((x.n * L + lp - L, C), dtype=q.dtype, device=dev))
+        sbuf, vtbuf, o, kbuf, tbuf = W.t[key]
+        ops.linear(t, wk, bias=bk, out=kbuf[: x.n * L], ldo=C)
+        if lp != L:  # the V^T GEMM likewise takes lp token rows per image (finite values in the spare columns, P is zero there)
+            tbuf[: x.n * L].copy_(t)
+            t = tbuf
         for i in range(x.n):
             rows = slice(i * L, (i + 1) * L)
-            ops.linear(q[rows], k[rows], out_f32=True, out_scale=C ** -0.5, out=sbuf[i], ldo=lp)   # [L, L]: q . k_j / sqrt(C)
+            ops.linear(q[rows], kbuf[i * L: i * L + lp], out_f32=True, out_scale=C ** -0.5, out=sbuf[i], ldo=lp)  # [L, lp]: q . k_j / sqrt(C)
             p = ops.softmax_rows(sbuf[i], L, lp)                                                    # bf16, padded keys get 0
-            ops.linear(wv, t[rows], out=vtbuf[i], ldo=lp)                                           # [C, L] = W_v X^T  (V^T, no bias)
+            ops.linear(wv, t[i * L: i * L + lp] if lp != L else t[rows], out=vtbuf[i], ldo=lp)      # [C, lp] = W_v X^T  (V^T, no bias)
             ops.linear(p, vtbuf[i], bias=bv, out=o[rows], ldo=C)                                    # P V + b_v (rows of P sum to 1)
         wo, bo = W.lin(a + ".to_out.0")
         out = ops.linear(o, wo, bias=bo, residual=x.data)

@@ -68,12 +68,12 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
         ops.gemm_conv(x, wt, **kw)
     torch.cuda.synchronize()
     if args.trace and (args.variant or int(os.environ.get("MDB_GEMM_VARIANT", "0"))) in (3, 4):
-        tr = torch.zeros(160 * 16, dtype=torch.int64, device=dev)
+        tr = torch.zeros(160 * 64, dtype=torch.int64, device=dev)
         if not args.warm:
             flush.zero_()
         ops.gemm_conv(x, wt, trace=tr, **kw)
         torch.cuda.synchronize()
-        tr = tr.view(160, 16).cpu()
+        tr = tr.view(160, 64).cpu()
         live = [i for i in range(160) if tr[i, 0] != 0]
         t0 = min(int(tr[i, 0]) for i in live)
         names = ["entry", "setup", "tma_end", "mma_end", "aux_stores_issued", "aux_drained", "epi_end", "mma_tile0", "epi_tile0",
@@ -82,6 +82,16 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
         dur = sorted(live, key=lambda i: int(tr[i, 10]))
         for cta in [live[0], live[1], dur[len(dur) // 2], dur[-2], dur[-1]]:
             print(f"   cta {cta:3d}: " + " ".join(f"{n}={int(tr[cta, i]) - t0 if tr[cta, i] else -1}" for i, n in enumerate(names)))
+        # chunk-level stamps of the first epilogue warp (its first two tiles): accumulator ready, then per chunk it owns
+        # (staging box ready, accumulator read, result stored, arrived)
+        for cta in [live[0], dur[-1]]:
+            for tile in range(2):
+                row = [int(tr[cta, 16 + tile * 20 + i]) for i in range(17)]
+                if row[0] == 0:
+                    continue
+                chunks = [row[1 + 4 * c: 5 + 4 * c] for c in range(4) if row[1 + 4 * c]]
+                print(f"   cta {cta:3d} warp 3 tile {tile}: acc_full={row[0] - t0}  " +
+                      "  ".join("[" + " ".join(str(v - t0) if v else "-" for v in ch) + "]" for ch in chunks))
         continue
     if args.trace:
         tr = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
