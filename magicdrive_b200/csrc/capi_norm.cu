@@ -282,15 +282,15 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 
 
 // ---- GroupNorm, pixel-major on a thread-block cluster per image (MDB_GN_ROWS=1 forces it, =0 disables it).  The image's
-// pixels are split into contiguous runs, one per CTA of the cluster.  A CTA pulls its run into shared memory ONCE with
-// one bulk-async copy per pixel row and source (cp.async.bulk, no registers, every byte in flight at once: the per-thread
-// 16-byte-load loop of the first cluster kernel was latency-bound at ~0.8 TB/s), computes per-group (mean, M2) of the run
-// exactly (two passes over shared memory), publishes them in its own shared memory, and after ONE cluster barrier combines
-// the runs of the image through distributed shared memory (Chan's parallel variance: no E[x^2] - mean^2 cancellation),
-// normalises its run from shared memory (+ affine, + SiLU) and stores it with coalesced 16-byte stores.  One global read
-// and one global write per element, both in full rows; gn_fused_kernel reads 20..80-byte channel slices per pixel instead.
-// blockDim = vpp * R (vpp = 16-byte vectors per pixel), thread = (pixel lane r, channel vector cv): a thread's 8 channels,
-// their groups, gamma and beta are fixed for the whole kernel.
+// pixels are split into contiguous runs, one per CTA of the cluster.  A CTA pulls its run into shared memory ONCE with bulk-async
+// copies (cp.async.bulk: no registers, every byte in flight at once -- the per-thread 16-byte-load loop of the first cluster
+// kernel was latency-bound at ~0.8 TB/s; a dense source is a handful of 16 KB copies, a strided one a copy per pixel row),
+// computes per-group (mean, M2) of the run exactly (two passes over shared memory), publishes them in its own shared memory,
+// and after ONE cluster barrier combines the runs of the image through distributed shared memory (Chan's parallel variance:
+// no E[x^2] - mean^2 cancellation), normalises its run from shared memory (+ affine, + SiLU) and stores it with coalesced
+// 16-byte stores.  One global read and one global write per element, both in full rows; gn_fused_kernel reads 20..80-byte
+// channel slices per pixel instead.  blockDim = vpp * R (vpp = 16-byte vectors per pixel), thread = (pixel lane r, channel
+// vector cv): a thread's 8 channels, their groups, gamma and beta are fixed for the whole kernel.
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
@@ -301,7 +301,7 @@ __global__ void gn_rows_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
                                const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ out, int ldo, int vpp, int R,
                                int ctas_per_img, int pix_per_cta) {
   using namespace mdb;
-  extern __shared__ __align__(128) uint4 gslab[];  // [pix_per_cta][vpp] then float red[R][ctot]
+  extern __shared__ __align__(128) uint4 gslab[];  // [pix_per_cta][c0] | [pix_per_cta][c1] bf16, then float red[R][ctot]
   const int ctot = c0 + c1, cpg = ctot / groups;
   float* red = reinterpret_cast<float*>(gslab + static_cast<size_t>(pix_per_cta) * vpp);  // [R][ctot]
   __shared__ float g_a[128], g_b[128];  // per group: mean / rstd of the image
@@ -313,6 +313,10 @@ __global__ void gn_rows_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
   const int cv = threadIdx.x % vpp, r0 = threadIdx.x / vpp;
   const int ch = cv * 8;
   const long long pix0 = static_cast<long long>(img) * hw + p_begin;
+  // this thread's 8 channels inside the slab of their source: element p of the run at mine[p * pitch]
+  const int vpp0 = c0 / 8;
+  const uint4* mine = (ch < c0) ? gslab + cv : gslab + static_cast<size_t>(pix_per_cta) * vpp0 + (cv - vpp0);
+  const int pitch = (ch < c0) ? vpp0 : vpp - vpp0;
   if (threadIdx.x == 0) {
     mbar_init(&full_bar, 1);
     fence_barrier_init();
@@ -321,23 +325,39 @@ __global__ void gn_rows_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
   __syncthreads();
   pdl_wait();  // everything above overlapped the producer's tail
   pdl_launch_dependents();
-  // ---- one bulk copy per pixel row and source; all complete on full_bar
-  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
-    const uint32_t dst = smem_u32(gslab) + static_cast<uint32_t>(p) * ctot * 2;
-    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(x0 + (pix0 + p) * ld0), "r"(c0 * 2), "r"(smem_u32(&full_bar))
-                 : "memory");
-    if (c1 > 0)
-      asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + c0 * 2),
-                   "l"(x1 + (pix0 + p) * ld1), "r"(c1 * 2), "r"(smem_u32(&full_bar))
-                   : "memory");
+  // ---- the run of each source lands in its own slab ([pixel][c0] then [pixel][c1]): a dense source (row stride == channels,
+  // every activation of the step) is ONE contiguous range, fetched as 16 KB bulk copies; a strided one row by row.
+  // All copies complete on full_bar.
+  {
+    const uint32_t bar = smem_u32(&full_bar);
+    auto fetch = [&](const __nv_bfloat16* src, int c, int ld, uint32_t dst) {
+      if (c == 0) return;
+      if (ld == c) {
+        const uint32_t bytes = static_cast<uint32_t>(npix) * c * 2;
+        const char* g = reinterpret_cast<const char*>(src + pix0 * ld);
+        for (uint32_t off = threadIdx.x * 16384u; off < bytes; off += blockDim.x * 16384u) {
+          const uint32_t n = min(16384u, bytes - off);
+          asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                       "l"(g + off), "r"(n), "r"(bar)
+                       : "memory");
+        }
+      } else {
+        for (int p = threadIdx.x; p < npix; p += blockDim.x)
+          asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           dst + static_cast<uint32_t>(p) * c * 2),
+                       "l"(src + (pix0 + p) * ld), "r"(c * 2), "r"(bar)
+                       : "memory");
+      }
+    };
+    fetch(x0, c0, ld0, smem_u32(gslab));
+    fetch(x1, c1, ld1, smem_u32(gslab) + static_cast<uint32_t>(pix_per_cta) * c0 * 2);
   }
   mbar_wait(&full_bar, 0);
   // ---- per-channel sums of the run -> per-group local mean
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int p = r0; p < npix; p += R) {
     float f[8];
-    unpack8(gslab[p * vpp + cv], f);
+    unpack8(mine[p * pitch], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += f[e];
   }
@@ -363,7 +383,7 @@ __global__ void gn_rows_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
   for (int e = 0; e < 8; ++e) lm[e] = part[2 * ((ch + e) / cpg)], acc[e] = 0.f;
   for (int p = r0; p < npix; p += R) {
     float f[8];
-    unpack8(gslab[p * vpp + cv], f);
+    unpack8(mine[p * pitch], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float d = f[e] - lm[e];
@@ -425,7 +445,7 @@ __global__ void gn_rows_kernel(const __nv_bfloat16* __restrict__ x0, int c0, int
   __nv_bfloat16* dst = out + pix0 * ldo + ch;
   for (int p = r0; p < npix; p += R) {
     float f[8];
-    unpack8(gslab[p * vpp + cv], f);
+    unpack8(mine[p * pitch], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float y = fmaf(f[e], sa[e], sb[e]);
@@ -475,35 +495,32 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
       }
       int cpi = 0, ppc = 0;
       size_t smem = 0;
-      auto need_for = [&](int cand, int& pp) {
-        pp = (hw + cand - 1) / cand;
-        return static_cast<size_t>(pp) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
-      };
-      for (int cand = 8; cand >= 1; cand /= 2) {
-        int pp;
-        const size_t need = need_for(cand, pp);
-        if (need > kMaxSmem) break;  // smaller clusters need even more
-        if ((pp >= 2 * R || cand == 1) && (cand - 1) * pp < hw) {
-          cpi = cand, ppc = pp, smem = need;
-          break;
-        }
-      }
-      if (cpi == 0 && max16 > 0) {
-        int pp;
-        const size_t need = need_for(16, pp);
-        if (need <= kMaxSmem && 15 * pp < hw) {
+      auto try_cluster = [&](int cand, bool allow_small_runs) {
+        const int pp = (hw + cand - 1) / cand;
+        const size_t need = static_cast<size_t>(pp) * ctot * 2 + static_cast<size_t>(R) * ctot * 4;
+        if (need > kMaxSmem || (cand - 1) * pp >= hw) return false;   // does not fit / would leave an empty run
+        if (!allow_small_runs && pp < 2 * R && cand > 1) return false;  // every pixel lane should get two pixels
+        if (cand > 8) {  // non-portable size: ask the driver whether such a cluster can be co-scheduled at all
+          if (max16 <= 0) return false;
           cudaLaunchConfig_t probe = {};
-          probe.gridDim = dim3(16 * n_img), probe.blockDim = dim3(vpp * R), probe.dynamicSmemBytes = need;
+          probe.gridDim = dim3(cand * n_img), probe.blockDim = dim3(vpp * R), probe.dynamicSmemBytes = need;
           cudaLaunchAttribute pa[1];
           pa[0].id = cudaLaunchAttributeClusterDimension;
-          pa[0].val.clusterDim.x = 16, pa[0].val.clusterDim.y = 1, pa[0].val.clusterDim.z = 1;
+          pa[0].val.clusterDim.x = cand, pa[0].val.clusterDim.y = 1, pa[0].val.clusterDim.z = 1;
           probe.attrs = pa, probe.numAttrs = 1;
           int n_clusters = 0;
-          if (cudaOccupancyMaxActiveClusters(&n_clusters, gn_rows_kernel, &probe) == cudaSuccess && n_clusters >= 1)
-            cpi = 16, ppc = pp, smem = need;
+          const bool ok = cudaOccupancyMaxActiveClusters(&n_clusters, gn_rows_kernel, &probe) == cudaSuccess && n_clusters >= 1;
           cudaGetLastError();
+          if (!ok) return false;
         }
-      }
+        cpi = cand, ppc = pp, smem = need;
+        return true;
+      };
+      const char* cenv = getenv("MDB_GN_ROWS_CLUSTER");  // experiment knob: try this cluster size first
+      const int forced = cenv ? atoi(cenv) : 0;
+      bool found = forced >= 1 && forced <= 16 && try_cluster(forced, true);
+      for (int cand = 8; cand >= 1 && !found; cand /= 2) found = try_cluster(cand, false);
+      if (!found) found = try_cluster(16, true);
       if (cpi > 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cpi * n_img), cfg.blockDim = dim3(vpp * R), cfg.dynamicSmemBytes = smem, cfg.stream = st;

@@ -128,15 +128,15 @@ struct PairCfg {
   static constexpr int kNBuf = 7;               // 128-row x 32-column (64 B) staging boxes: residual in, result out
   static constexpr int kAhead = 4;              // how many chunks ahead of the store cursor buffers are prepared
   static constexpr int kBufBytes = 128 * 64;
-  static constexpr int kConstBytes = 2 * 2 * 256 * 4;  // [acc stage][bias+shift | colsum][BLOCK_N] fp32
+  static constexpr int kEpiGroups = MDB_EPI_GROUPS;  // groups of four epilogue warps (one warp per TMEM lane quarter)
+  static constexpr int kEpiWarps = 4 * kEpiGroups;
+  static constexpr int kConstBytes = kEpiWarps * 512;  // one 512-byte slot of column constants per epilogue warp
   static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 232448 - 1024 - kBarBytes - kConstBytes - kNBuf * kBufBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStride = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128) ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kEpiGroups = MDB_EPI_GROUPS;  // groups of four epilogue warps (one warp per TMEM lane quarter)
-  static constexpr int kEpiWarps = 4 * kEpiGroups;
   static constexpr int kThreads = 96 + 32 * kEpiWarps;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNBuf * kBufBytes + kConstBytes + kBarBytes + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -389,7 +389,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // arithmetic on fp32 PAIRS (FFMA2 / FADD2 / FMUL2): out = A_row * acc + (B_row * colsum_n + bias_n) [+ residual] with
     // A_row = rstd * scale, B_row = -mean * rstd * scale (folded LayerNorm) or A_row = scale, B_row = 0.
     constexpr int G = Cfg::kEpiGroups;
-    constexpr int NEPI = 128 * G;
     const int q = warp & 3;
     const int eg = (warp - 3) >> 2;
     const int row = q * 32 + lane;
@@ -438,38 +437,44 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (j < pp.ln_parts) pf[j] = __ldg(sp + j);
       }
     };
-    // bias (+ per-image shift) and folded-LayerNorm column sums of four consecutive columns: warp-uniform 16-byte loads
-    // straight from global memory (L1 hits after the first warp): no shared staging, no CTA-wide barrier per tile
-    auto col_consts = [&](const float* rowb, int n, unsigned long long B2, unsigned long long& t0, unsigned long long& t1) {
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-      if (rowb) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(rowb + n));
-        b.x += r.x, b.y += r.y, b.z += r.z, b.w += r.w;
-      }
-      if (scale != 1.f) b.x *= scale, b.y *= scale, b.z *= scale, b.w *= scale;
-      t0 = pk2(b.x, b.y), t1 = pk2(b.z, b.w);
-      if (has_ln) {
-        const float4 cs = __ldg(reinterpret_cast<const float4*>(pp.ln_colsum + n));
-        t0 = fma2(B2, pk2(cs.x, cs.y), t0), t1 = fma2(B2, pk2(cs.z, cs.w), t1);
-      }
+    // Column constants of a chunk -- bias (+ per-image shift) and folded-LayerNorm column sums, for GEGLU of the value AND the
+    // gate columns -- are fetched ONE OWNED CHUNK AHEAD, one column per lane (a coalesced 128-byte load per array: an L2 round
+    // trip, ~0.6 us, that the chunk in between hides; fetched at use it cost every chunk that round trip), parked in four
+    // registers, and spread to the whole warp through a private 512-byte shared slot (no barrier beyond __syncwarp).
+    const uint32_t cslot = smem_u32(smC) + static_cast<uint32_t>(warp - 3) * 512;
+    constexpr int HALFN = BLOCK_N / 2;
+    float kc[4] = {0.f, 0.f, 0.f, 0.f};  // [bias' | colsum] of the value / plain columns, then of the gate columns
+    int kc_t = -1, kc_c = -1;            // the (tile, chunk) they belong to
+    auto load_consts = [&](int t, const TileRow& r, int c) {
+      const float* rowb = p.rowbias ? p.rowbias + static_cast<long long>(r.img_tile) * p.rowbias_ld : nullptr;
+      const int n = r.nt * BLOCK_N + c * 32 + lane;
+      auto one = [&](int col, float& b, float& cs) {
+        b = p.bias ? __ldg(p.bias + col) : 0.f;
+        if (rowb) b += __ldg(rowb + col);
+        b *= scale;
+        cs = has_ln ? __ldg(pp.ln_colsum + col) : 0.f;
+      };
+      one(n, kc[0], kc[1]);
+      if (geglu) one(n + HALFN, kc[2], kc[3]);
+      kc_t = t, kc_c = c;
     };
-    // the constants of a tile are pulled into L1 a whole tile ahead (first touch per SM would otherwise cost every chunk an
-    // L2 round trip): lane l of one warp covers columns [32 l, 32 l + 32) = one 128-byte line per array
-    auto prefetch_consts = [&](const TileRow& r, int t) {
-      if (warp != 3 || t >= total) return;
-      const int n = r.nt * BLOCK_N + lane * 32;
-      if (lane * 32 < BLOCK_N && n < p.n_out) {
-        if (p.bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n));
-        if (has_ln) asm volatile("prefetch.global.L1 [%0];" ::"l"(pp.ln_colsum + n));
-        if (p.rowbias) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.rowbias + static_cast<long long>(r.img_tile) * p.rowbias_ld + n));
-      }
+    // first chunk of tile (t, gk0 = running chunk number at its start) owned by this group, or -1
+    auto first_owned = [&](int gk0, int nch) {
+      const int c = ((eg - gk0) % G + G) % G;
+      return c < nch ? c : -1;
+    };
+    auto chunks_of = [&](const TileRow& r) {
+      const int left = (pp.out_cols - r.nt * out_per_tile) / 32;
+      return left < ch_tile ? left : ch_tile;
     };
     TileRow cur = locate(cluster_id);
-    prefetch_consts(cur, cluster_id);
     fetch_stats(cur);
     int it = 0;
     int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
+    if (cluster_id < total) {
+      const int c0 = first_owned(0, chunks_of(cur));
+      if (c0 >= 0) load_consts(cluster_id, cur, c0);
+    }
     for (int t = cluster_id; t < total; t += n_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -493,12 +498,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       // next tile's position / statistics: loads in flight while this tile is processed
       const TileRow nxt = locate(t + n_clusters);
-      prefetch_consts(nxt, t + n_clusters);
       fetch_stats(nxt);
-      const int nbase = cur.nt * BLOCK_N;
-      const float* rowb = p.rowbias ? p.rowbias + static_cast<long long>(cur.img_tile) * p.rowbias_ld : nullptr;
-      const int left = (pp.out_cols - cur.nt * out_per_tile) / 32;
-      const int nch = left < ch_tile ? left : ch_tile;
+      const int nch = chunks_of(cur);
+      const int gk_tile = gk;  // running chunk number of this tile's chunk 0
       const unsigned long long A2 = pk2(rowA, rowA), B2 = pk2(rowB, rowB);
       unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
       mbar_wait(&acc_full[as], aphase);
@@ -512,16 +514,41 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int tslot_end = tslot + 16;
 #define MDB_TRACE_CHUNK() do { if (tslot >= 0 && tslot < tslot_end) { MDB_TRACE3(tslot); ++tslot; } } while (0)
 
-      for (int c = 0; c < nch; ++c, ++gk) {
-        if ((gk % G) != eg) continue;  // round-robin over the running chunk number: balanced even when a tile has 5 chunks
+      // the chunks go round-robin over the running chunk number to the groups: balanced even when a tile has 5 chunks
+      for (int c = first_owned(gk_tile, nch); c >= 0 && c < nch; c += G) {
+        gk = gk_tile + c;
         const int buf = gk % NBUF;
         const uint32_t srow = my_row + buf * Cfg::kBufBytes;
+        // this chunk's constants (normally fetched during the previous owned chunk) -> the warp's slot; then start the fetch
+        // for the next owned chunk, in this tile or at the head of the next one
+        if (kc_t != t || kc_c != c) load_consts(t, cur, c);
+        __syncwarp();  // every lane has finished reading the slot's previous contents
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + lane * 4), "f"(kc[0]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 128 + lane * 4), "f"(kc[1]) : "memory");
+        if (geglu) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 256 + lane * 4), "f"(kc[2]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 384 + lane * 4), "f"(kc[3]) : "memory");
+        }
+        __syncwarp();
+        if (c + G < nch) {
+          load_consts(t, cur, c + G);
+        } else if (t + n_clusters < total) {
+          const int cn = first_owned(gk_tile + nch, chunks_of(nxt));
+          if (cn >= 0) load_consts(t + n_clusters, nxt, cn);
+        }
         if (!geglu) {
           uint32_t v[32];
-          tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while the constants are fetched and the staging box is awaited
+          tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while the constants are combined and the staging box is awaited
           unsigned long long pre[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) col_consts(rowb, nbase + c * 32 + 4 * j, B2, pre[2 * j], pre[2 * j + 1]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = lds_f4(cslot + 16 * j);
+            pre[2 * j] = pk2(b.x, b.y), pre[2 * j + 1] = pk2(b.z, b.w);
+            if (has_ln) {
+              const float4 cs = lds_f4(cslot + 128 + 16 * j);
+              pre[2 * j] = fma2(B2, pk2(cs.x, cs.y), pre[2 * j]), pre[2 * j + 1] = fma2(B2, pk2(cs.z, cs.w), pre[2 * j + 1]);
+            }
+          }
           mbar_wait(&res_full[buf], (gk / NBUF) & 1);
           MDB_TRACE_CHUNK();
           uint4 r[4];
@@ -558,8 +585,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             unsigned long long tv[8], tg[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              col_consts(rowb, nbase + c * 32 + hh * 16 + 4 * j, B2, tv[2 * j], tv[2 * j + 1]);
-              col_consts(rowb, nbase + HALF + c * 32 + hh * 16 + 4 * j, B2, tg[2 * j], tg[2 * j + 1]);
+              const float4 bv = lds_f4(cslot + hh * 64 + 16 * j), bg = lds_f4(cslot + 256 + hh * 64 + 16 * j);
+              tv[2 * j] = pk2(bv.x, bv.y), tv[2 * j + 1] = pk2(bv.z, bv.w);
+              tg[2 * j] = pk2(bg.x, bg.y), tg[2 * j + 1] = pk2(bg.z, bg.w);
+              if (has_ln) {
+                const float4 sv = lds_f4(cslot + 128 + hh * 64 + 16 * j), sg = lds_f4(cslot + 384 + hh * 64 + 16 * j);
+                tv[2 * j] = fma2(B2, pk2(sv.x, sv.y), tv[2 * j]), tv[2 * j + 1] = fma2(B2, pk2(sv.z, sv.w), tv[2 * j + 1]);
+                tg[2 * j] = fma2(B2, pk2(sg.x, sg.y), tg[2 * j]), tg[2 * j + 1] = fma2(B2, pk2(sg.z, sg.w), tg[2 * j + 1]);
+              }
             }
             tmem_ld_wait();
 #pragma unroll
@@ -584,6 +617,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (!geglu) MDB_TRACE_CHUNK();
       }
 #undef MDB_TRACE_CHUNK
+      gk = gk_tile + nch;
       if (pp.stats_out && cur.ok) {
         float s0, s1, q0, q1;
         upk2(st_s2, s0, s1);

@@ -82,3 +82,60 @@ def test_row_location_matches_reference_decomposition():
                 th = a - tn * tiles_h
                 assert nt == t // m_groups
                 assert (tw, th, tn) == (mt % tiles_w, (mt // tiles_w) % tiles_h, mt // (tiles_w * tiles_h))
+
+
+def _owned_chunks(eg, G, tiles):
+    """Mirror of the epilogue's chunk loop + one-chunk-ahead constant fetch (gemm_pair.cuh): yields (gk, t, c, prefetched)."""
+    def first_owned(gk0, nch):
+        c = ((eg - gk0) % G + G) % G
+        return c if c < nch else -1
+
+    gk = 0
+    kc = None
+    if tiles:
+        c0 = first_owned(0, tiles[0][2])
+        if c0 >= 0:
+            kc = (tiles[0][0], c0)
+    for i, (t, _, nch) in enumerate(tiles):
+        gk_tile = gk
+        c = first_owned(gk_tile, nch)
+        while 0 <= c < nch:
+            hit = kc == (t, c)
+            yield gk_tile + c, t, c, hit
+            if c + G < nch:
+                kc = (t, c + G)
+            elif i + 1 < len(tiles):
+                cn = first_owned(gk_tile + nch, tiles[i + 1][2])
+                if cn >= 0:
+                    kc = (tiles[i + 1][0], cn)
+            c += G
+        gk = gk_tile + nch
+
+
+def test_groups_partition_the_chunk_sequence_and_prefetch_hits():
+    rng = random.Random(3)
+    for _ in range(300):
+        G = rng.choice([2, 3, 4])
+        n_tiles_seq = rng.randrange(1, 12)
+        tiles = [(7 + 13 * i, 0, rng.choice([1, 2, 3, 4, 5, 8])) for i in range(n_tiles_seq)]
+        total_chunks = sum(n for _, _, n in tiles)
+        seen = {}
+        misses = 0
+        for eg in range(G):
+            last = -1
+            for gk, t, c, hit in _owned_chunks(eg, G, tiles):
+                assert gk % G == eg and gk > last
+                last = gk
+                assert gk not in seen
+                seen[gk] = (t, c)
+                misses += (not hit)
+        assert sorted(seen) == list(range(total_chunks))
+        # the manager numbers chunks tile after tile
+        k = 0
+        for t, _, nch in tiles:
+            for c in range(nch):
+                assert seen[k] == (t, c)
+                k += 1
+        # a fetch-at-use only happens after a tile in which the group owned nothing
+        if all(n >= G for _, _, n in tiles):
+            assert misses == 0

@@ -14,8 +14,12 @@ SHAPES = [(12, 1400, 320, 0), (12, 1400, 320, 320), (12, 1400, 640, 320), (12, 3
           (12, 28, 1280, 0), (12, 28, 1280, 1280)]
 
 
-def time_mode(mode, n, hw, c0, c1, iters=40):
+def time_mode(mode, n, hw, c0, c1, iters=40, cluster=None):
     os.environ["MDB_GN_ROWS"] = mode
+    if cluster:
+        os.environ["MDB_GN_ROWS_CLUSTER"] = str(cluster)
+    else:
+        os.environ.pop("MDB_GN_ROWS_CLUSTER", None)
     g = torch.Generator(device="cuda").manual_seed(1)
     xa = torch.randn(n * hw, c0, device="cuda", generator=g).bfloat16()
     xb = torch.randn(n * hw, c1, device="cuda", generator=g).bfloat16() if c1 else None
@@ -41,8 +45,10 @@ def main():
         byts = 2 * n * hw * (c0 + c1) * 2
         t0, o0 = time_mode("0", n, hw, c0, c1)
         t1, o1 = time_mode("1", n, hw, c0, c1)
+        t12, _ = time_mode("1", n, hw, c0, c1, cluster=12)
+        t16, _ = time_mode("1", n, hw, c0, c1, cluster=16)
         print(f"n={n} hw={hw} c={c0}+{c1}:  fused {t0:7.1f} us {byts / t0 / 1e3:7.0f} GB/s   rows {t1:7.1f} us {byts / t1 / 1e3:7.0f} GB/s   "
-              f"diff {(o0 != o1).float().mean().item():.2e}")
+              f"rows/12 {t12:7.1f} us  rows/16 {t16:7.1f} us   diff {(o0 != o1).float().mean().item():.2e}")
 
 
 if __name__ == "__main__":
