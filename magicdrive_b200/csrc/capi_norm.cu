@@ -8,9 +8,15 @@
 #include "common_host.h"
 #include "ptx_cluster.cuh"
 
-// images of at least this many bytes take the pixel-major cluster GroupNorm (MDB_GN_ROWS unset)
+// Images of at least this many bytes take the pixel-major cluster GroupNorm when MDB_GN_ROWS is unset: measured crossover
+// against gn_fused_kernel on B200 (tools/bench_norm.py, profiles/gn_rows_r2.txt) -- 12 x 1400 x 320: 16.5 vs 21.4 us,
+// 12 x 350 x 1920: 20.5 vs 22.6 us, equal at 12 x 350 x 1280, slower below; inputs that only fit a 16-CTA cluster win from
+// 2.5 MB (12 x 1400 x 960: 39.0 vs 43.8 us; 12 x 1400 x 640 loses 30.9 vs 28.7 us).
 #ifndef MDB_GN_ROWS_MIN_BYTES
-#define MDB_GN_ROWS_MIN_BYTES (1LL << 62)
+#define MDB_GN_ROWS_MIN_BYTES 850000LL
+#endif
+#ifndef MDB_GN_ROWS_MIN_BYTES_C16
+#define MDB_GN_ROWS_MIN_BYTES_C16 2500000LL
 #endif
 
 namespace {
@@ -520,7 +526,7 @@ extern "C" int mdb_groupnorm(const void* x0, int c0, int ld0, const void* x1, in
       const int forced = cenv ? atoi(cenv) : 0;
       bool found = forced >= 1 && forced <= 16 && try_cluster(forced, true);
       for (int cand = 8; cand >= 1 && !found; cand /= 2) found = try_cluster(cand, false);
-      if (!found) found = try_cluster(16, true);
+      if (!found && (mode == 1 || img_bytes >= MDB_GN_ROWS_MIN_BYTES_C16)) found = try_cluster(16, true);
       if (cpi > 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cpi * n_img), cfg.blockDim = dim3(vpp * R), cfg.dynamicSmemBytes = smem, cfg.stream = st;

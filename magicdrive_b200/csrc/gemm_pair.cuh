@@ -443,19 +443,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // registers, and spread to the whole warp through a private 512-byte shared slot (no barrier beyond __syncwarp).
     const uint32_t cslot = smem_u32(smC) + static_cast<uint32_t>(warp - 3) * 512;
     constexpr int HALFN = BLOCK_N / 2;
-    float kc[4] = {0.f, 0.f, 0.f, 0.f};  // [bias' | colsum] of the value / plain columns, then of the gate columns
-    int kc_t = -1, kc_c = -1;            // the (tile, chunk) they belong to
+    // raw loaded values only: any arithmetic on them here would make the warp wait for the loads right away (the first version
+    // scaled the bias at load time and thereby paid the L2 round trip it was meant to hide)
+    float kb[2] = {0.f, 0.f}, kr[2] = {0.f, 0.f}, kcs[2] = {0.f, 0.f};  // bias, per-image shift, colsum of the [plain | gate] column
+    int kc_t = -1, kc_c = -1;                                          // the (tile, chunk) they belong to
     auto load_consts = [&](int t, const TileRow& r, int c) {
       const float* rowb = p.rowbias ? p.rowbias + static_cast<long long>(r.img_tile) * p.rowbias_ld : nullptr;
       const int n = r.nt * BLOCK_N + c * 32 + lane;
-      auto one = [&](int col, float& b, float& cs) {
-        b = p.bias ? __ldg(p.bias + col) : 0.f;
-        if (rowb) b += __ldg(rowb + col);
-        b *= scale;
-        cs = has_ln ? __ldg(pp.ln_colsum + col) : 0.f;
-      };
-      one(n, kc[0], kc[1]);
-      if (geglu) one(n + HALFN, kc[2], kc[3]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !geglu) break;
+        const int col = n + h * HALFN;
+        kb[h] = p.bias ? __ldg(p.bias + col) : 0.f;
+        kr[h] = rowb ? __ldg(rowb + col) : 0.f;
+        kcs[h] = has_ln ? __ldg(pp.ln_colsum + col) : 0.f;
+      }
       kc_t = t, kc_c = c;
     };
     // first chunk of tile (t, gk0 = running chunk number at its start) owned by this group, or -1
@@ -523,11 +525,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // for the next owned chunk, in this tile or at the head of the next one
         if (kc_t != t || kc_c != c) load_consts(t, cur, c);
         __syncwarp();  // every lane has finished reading the slot's previous contents
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + lane * 4), "f"(kc[0]) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 128 + lane * 4), "f"(kc[1]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + lane * 4), "f"((kb[0] + kr[0]) * scale) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 128 + lane * 4), "f"(kcs[0]) : "memory");
         if (geglu) {
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 256 + lane * 4), "f"(kc[2]) : "memory");
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 384 + lane * 4), "f"(kc[3]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 256 + lane * 4), "f"((kb[1] + kr[1]) * scale) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 384 + lane * 4), "f"(kcs[1]) : "memory");
         }
         __syncwarp();
         if (c + G < nch) {
