@@ -205,6 +205,9 @@ bool pair_supported(const mdb_gemm_desc* d, const Plan& box) {
   const int out_cols = d->epi_mode == 1 ? d->n_out / 2 : d->n_out;
   if (out_cols % 32 || d->n_out % 32) return false;
   if (d->rowbias && d->rowbias_ld != 0 && box.bn != 1) return false;
+  // bias / per-image shift / folded-LayerNorm column sums reach the epilogue as bulk copies of whole tiles: 16-byte alignment
+  auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+  if (misaligned(d->bias) || misaligned(d->rowbias) || misaligned(d->ln_colsum) || (d->rowbias && d->rowbias_ld % 4)) return false;
   return true;
 }
 

@@ -130,7 +130,8 @@ struct PairCfg {
   static constexpr int kBufBytes = 128 * 64;
   static constexpr int kEpiGroups = MDB_EPI_GROUPS;  // groups of four epilogue warps (one warp per TMEM lane quarter)
   static constexpr int kEpiWarps = 4 * kEpiGroups;
-  static constexpr int kConstBytes = kEpiWarps * 512;  // one 512-byte slot of column constants per epilogue warp
+  static constexpr int kConstStage = 3 * 256 * 4;      // [bias | per-image shift | LayerNorm column sums] x 256 fp32 of one tile
+  static constexpr int kConstBytes = 2 * kConstStage;  // double-buffered like the accumulators
   static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 232448 - 1024 - kBarBytes - kConstBytes - kNBuf * kBufBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
@@ -168,7 +169,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint64_t* res_full = acc_empty + 2;       // [NBUF]  staging box prepared (residual landed / buffer free)
   uint64_t* out_ready = res_full + NBUF;    // [NBUF]  staging box holds the finished bf16 chunk
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_ready + NBUF);
+  uint64_t* const_full = out_ready + NBUF;  // [2]  column constants of a tile landed (bulk copies by the manager)
+  uint64_t* const_empty = const_full + 2;   // [2]  every epilogue warp of this CTA is done with them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -212,6 +215,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], CTAS * Cfg::kEpiWarps);  // one arrive per epilogue warp of every CTA of the pair
+      mbar_init(&const_full[i], 1);
+      mbar_init(&const_empty[i], Cfg::kEpiWarps);
     }
     for (int i = 0; i < NBUF; ++i) {
       mbar_init(&res_full[i], 1);
@@ -355,6 +360,41 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           enter_tile(cu);
         }
       };
+      // Column constants (bias, per-image shift, folded-LayerNorm column sums) of tile ordinal `itn` -> smC[itn & 1] by bulk
+      // copies, a whole tile before the epilogue needs them: fetched by the epilogue warps themselves (even one chunk ahead)
+      // they cost every chunk ~0.5 us of exposed L2 latency (chunk-level trace).
+      auto load_tile_consts = [&](int itn) {
+        const int t = cluster_id + itn * n_clusters;
+        if (t >= total) return;
+        const int as = itn & 1;
+        if (itn >= 2) mbar_wait(&const_empty[as], ((itn >> 1) - 1) & 1);  // the epilogue is done with tile itn - 2
+        const int nt = t / pp.m_groups;
+        const int mt = (t - nt * pp.m_groups) * CTAS + static_cast<int>(rank);
+        const int img = min((mt / (p.tiles_w * p.tiles_h)) * p.bn, p.n_img - 1);
+        const int n0 = nt * BLOCK_N;
+        const int cnt = min(BLOCK_N, p.n_out - n0);
+        const uint32_t bytes = static_cast<uint32_t>(cnt) * 4;
+        const uint32_t dst = smem_u32(smC) + as * Cfg::kConstStage;
+        const uint32_t bar = smem_u32(&const_full[as]);
+        const bool has_ln = pp.ln_stats != nullptr;
+        const uint32_t tx = (p.bias ? bytes : 0u) + (p.rowbias ? bytes : 0u) + (has_ln ? bytes : 0u);
+        if (tx == 0) {
+          mbar_arrive(&const_full[as]);
+          return;
+        }
+        mbar_arrive_expect_tx(&const_full[as], tx);
+        auto copy = [&](uint32_t d, const float* src) {
+          asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+                       "r"(bytes), "r"(bar)
+                       : "memory");
+        };
+        if (p.bias) copy(dst, p.bias + n0);
+        if (p.rowbias) copy(dst + 1024, p.rowbias + static_cast<long long>(img) * p.rowbias_ld + n0);
+        if (has_ln) copy(dst + 2048, pp.ln_colsum + n0);
+      };
+      load_tile_consts(0);
+      load_tile_consts(1);
+      int sto_it = 0;  // tile ordinal of the store cursor
       Cursor pre{cluster_id, 0, 0, 0, 0, 0, 0, 0, false}, sto{cluster_id, 0, 0, 0, 0, 0, 0, 0, false};
       enter_tile(pre);
       enter_tile(sto);
@@ -376,7 +416,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(&out_ready[buf], (sto.k / NBUF) & 1);
         if (sto.real) tma_store_4d(&tmOut, smO + buf * Cfg::kBufBytes, sto.col0 + sto.c * 32, sto.w0, sto.h0, sto.img0);
         bulk_commit_group();  // one group per chunk (empty for the phantom half of an odd pair) keeps the wait counts exact
+        const int t_before = sto.t;
         advance(sto);
+        if (sto.t != t_before) {  // the last chunk of tile sto_it is on its way out: its constant buffer is about to be free
+          load_tile_consts(sto_it + 2);
+          ++sto_it;
+        }
       }
       MDB_TRACE3(4);
       bulk_wait_group_all();
@@ -437,28 +482,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (j < pp.ln_parts) pf[j] = __ldg(sp + j);
       }
     };
-    // Column constants of a chunk -- bias (+ per-image shift) and folded-LayerNorm column sums, for GEGLU of the value AND the
-    // gate columns -- are fetched ONE OWNED CHUNK AHEAD, one column per lane (a coalesced 128-byte load per array: an L2 round
-    // trip, ~0.6 us, that the chunk in between hides; fetched at use it cost every chunk that round trip), parked in four
-    // registers, and spread to the whole warp through a private 512-byte shared slot (no barrier beyond __syncwarp).
-    const uint32_t cslot = smem_u32(smC) + static_cast<uint32_t>(warp - 3) * 512;
+    // Column constants of a tile sit in smC[as] (bulk-copied by the manager one tile ahead): broadcast LDS.128 reads.
+    // t0/t1 = (bias + shift) * scale [+ B_row * colsum] for columns col .. col + 3 of the tile.
     constexpr int HALFN = BLOCK_N / 2;
-    // raw loaded values only: any arithmetic on them here would make the warp wait for the loads right away (the first version
-    // scaled the bias at load time and thereby paid the L2 round trip it was meant to hide)
-    float kb[2] = {0.f, 0.f}, kr[2] = {0.f, 0.f}, kcs[2] = {0.f, 0.f};  // bias, per-image shift, colsum of the [plain | gate] column
-    int kc_t = -1, kc_c = -1;                                          // the (tile, chunk) they belong to
-    auto load_consts = [&](int t, const TileRow& r, int c) {
-      const float* rowb = p.rowbias ? p.rowbias + static_cast<long long>(r.img_tile) * p.rowbias_ld : nullptr;
-      const int n = r.nt * BLOCK_N + c * 32 + lane;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !geglu) break;
-        const int col = n + h * HALFN;
-        kb[h] = p.bias ? __ldg(p.bias + col) : 0.f;
-        kr[h] = rowb ? __ldg(rowb + col) : 0.f;
-        kcs[h] = has_ln ? __ldg(pp.ln_colsum + col) : 0.f;
+    const bool has_rowb = p.rowbias != nullptr, has_bias = p.bias != nullptr;
+    auto col_consts = [&](uint32_t cst, int col, unsigned long long B2, unsigned long long& t0, unsigned long long& t1) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bias) b = lds_f4(cst + col * 4);
+      if (has_rowb) {
+        const float4 r = lds_f4(cst + 1024 + col * 4);
+        b.x += r.x, b.y += r.y, b.z += r.z, b.w += r.w;
       }
-      kc_t = t, kc_c = c;
+      t0 = pk2(b.x, b.y), t1 = pk2(b.z, b.w);
+      if (scale != 1.f) t0 = mul2(t0, pk2(scale, scale)), t1 = mul2(t1, pk2(scale, scale));
+      if (has_ln) {
+        const float4 cs = lds_f4(cst + 2048 + col * 4);
+        t0 = fma2(B2, pk2(cs.x, cs.y), t0), t1 = fma2(B2, pk2(cs.z, cs.w), t1);
+      }
     };
     // first chunk of tile (t, gk0 = running chunk number at its start) owned by this group, or -1
     auto first_owned = [&](int gk0, int nch) {
@@ -473,10 +513,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     fetch_stats(cur);
     int it = 0;
     int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
-    if (cluster_id < total) {
-      const int c0 = first_owned(0, chunks_of(cur));
-      if (c0 >= 0) load_consts(cluster_id, cur, c0);
-    }
     for (int t = cluster_id; t < total; t += n_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -505,6 +541,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int gk_tile = gk;  // running chunk number of this tile's chunk 0
       const unsigned long long A2 = pk2(rowA, rowA), B2 = pk2(rowB, rowB);
       unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
+      const uint32_t cst = smem_u32(smC) + as * Cfg::kConstStage;
+      mbar_wait(&const_full[as], aphase);  // landed a tile ago
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
@@ -521,36 +559,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         gk = gk_tile + c;
         const int buf = gk % NBUF;
         const uint32_t srow = my_row + buf * Cfg::kBufBytes;
-        // this chunk's constants (normally fetched during the previous owned chunk) -> the warp's slot; then start the fetch
-        // for the next owned chunk, in this tile or at the head of the next one
-        if (kc_t != t || kc_c != c) load_consts(t, cur, c);
-        __syncwarp();  // every lane has finished reading the slot's previous contents
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + lane * 4), "f"((kb[0] + kr[0]) * scale) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 128 + lane * 4), "f"(kcs[0]) : "memory");
-        if (geglu) {
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 256 + lane * 4), "f"((kb[1] + kr[1]) * scale) : "memory");
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cslot + 384 + lane * 4), "f"(kcs[1]) : "memory");
-        }
-        __syncwarp();
-        if (c + G < nch) {
-          load_consts(t, cur, c + G);
-        } else if (t + n_clusters < total) {
-          const int cn = first_owned(gk_tile + nch, chunks_of(nxt));
-          if (cn >= 0) load_consts(t + n_clusters, nxt, cn);
-        }
         if (!geglu) {
           uint32_t v[32];
           tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while the constants are combined and the staging box is awaited
           unsigned long long pre[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = lds_f4(cslot + 16 * j);
-            pre[2 * j] = pk2(b.x, b.y), pre[2 * j + 1] = pk2(b.z, b.w);
-            if (has_ln) {
-              const float4 cs = lds_f4(cslot + 128 + 16 * j);
-              pre[2 * j] = fma2(B2, pk2(cs.x, cs.y), pre[2 * j]), pre[2 * j + 1] = fma2(B2, pk2(cs.z, cs.w), pre[2 * j + 1]);
-            }
-          }
+          for (int j = 0; j < 8; ++j) col_consts(cst, c * 32 + 4 * j, B2, pre[2 * j], pre[2 * j + 1]);
           mbar_wait(&res_full[buf], (gk / NBUF) & 1);
           MDB_TRACE_CHUNK();
           uint4 r[4];
@@ -587,14 +601,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             unsigned long long tv[8], tg[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 bv = lds_f4(cslot + hh * 64 + 16 * j), bg = lds_f4(cslot + 256 + hh * 64 + 16 * j);
-              tv[2 * j] = pk2(bv.x, bv.y), tv[2 * j + 1] = pk2(bv.z, bv.w);
-              tg[2 * j] = pk2(bg.x, bg.y), tg[2 * j + 1] = pk2(bg.z, bg.w);
-              if (has_ln) {
-                const float4 sv = lds_f4(cslot + 128 + hh * 64 + 16 * j), sg = lds_f4(cslot + 384 + hh * 64 + 16 * j);
-                tv[2 * j] = fma2(B2, pk2(sv.x, sv.y), tv[2 * j]), tv[2 * j + 1] = fma2(B2, pk2(sv.z, sv.w), tv[2 * j + 1]);
-                tg[2 * j] = fma2(B2, pk2(sg.x, sg.y), tg[2 * j]), tg[2 * j + 1] = fma2(B2, pk2(sg.z, sg.w), tg[2 * j + 1]);
-              }
+              col_consts(cst, c * 32 + hh * 16 + 4 * j, B2, tv[2 * j], tv[2 * j + 1]);
+              col_consts(cst, HALFN + c * 32 + hh * 16 + 4 * j, B2, tg[2 * j], tg[2 * j + 1]);
             }
             tmem_ld_wait();
 #pragma unroll
@@ -628,12 +636,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         reinterpret_cast<float2*>(pp.stats_out)[(static_cast<long long>(cur.pix) * pp.n_tiles + cur.nt) * G + eg] =
             make_float2(s0 + s1, q0 + q1);
       }
-      // release this accumulator stage to the MMA warp of the leader CTA
+      // release this accumulator stage to the MMA warp of the leader CTA, and the constants' buffer to the manager
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
         else mbar_arrive(&acc_empty[as]);
+        mbar_arrive(&const_empty[as]);
       }
       cur = nxt;
       if (warp == 3 && lane == 0 && it == 0) MDB_TRACE3(8);
@@ -643,7 +652,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   __syncwarp();
   if (threadIdx.x == 0) MDB_TRACE3(9);
-  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  // both CTAs are done with each other's barriers and with TMEM: liveness only, no memory ordering needed
+  if constexpr (PAIR) cluster_sync_relaxed(); else __syncthreads();
   if (threadIdx.x == 0) MDB_TRACE3(10);
 #undef MDB_TRACE3
   if (warp == 2) {

@@ -85,57 +85,53 @@ def test_row_location_matches_reference_decomposition():
 
 
 def _owned_chunks(eg, G, tiles):
-    """Mirror of the epilogue's chunk loop + one-chunk-ahead constant fetch (gemm_pair.cuh): yields (gk, t, c, prefetched)."""
-    def first_owned(gk0, nch):
-        c = ((eg - gk0) % G + G) % G
-        return c if c < nch else -1
-
+    """Mirror of the epilogue's chunk loop (gemm_pair.cuh): yields (gk, t, c) for the chunks warp group `eg` processes."""
     gk = 0
-    kc = None
-    if tiles:
-        c0 = first_owned(0, tiles[0][2])
-        if c0 >= 0:
-            kc = (tiles[0][0], c0)
-    for i, (t, _, nch) in enumerate(tiles):
-        gk_tile = gk
-        c = first_owned(gk_tile, nch)
-        while 0 <= c < nch:
-            hit = kc == (t, c)
-            yield gk_tile + c, t, c, hit
-            if c + G < nch:
-                kc = (t, c + G)
-            elif i + 1 < len(tiles):
-                cn = first_owned(gk_tile + nch, tiles[i + 1][2])
-                if cn >= 0:
-                    kc = (tiles[i + 1][0], cn)
+    for t, _, nch in tiles:
+        c = ((eg - gk) % G + G) % G
+        while c < nch:
+            yield gk + c, t, c
             c += G
-        gk = gk_tile + nch
+        gk += nch
 
 
-def test_groups_partition_the_chunk_sequence_and_prefetch_hits():
+def test_groups_partition_the_chunk_sequence():
     rng = random.Random(3)
     for _ in range(300):
         G = rng.choice([2, 3, 4])
-        n_tiles_seq = rng.randrange(1, 12)
-        tiles = [(7 + 13 * i, 0, rng.choice([1, 2, 3, 4, 5, 8])) for i in range(n_tiles_seq)]
+        tiles = [(7 + 13 * i, 0, rng.choice([1, 2, 3, 4, 5, 8])) for i in range(rng.randrange(1, 12))]
         total_chunks = sum(n for _, _, n in tiles)
         seen = {}
-        misses = 0
         for eg in range(G):
             last = -1
-            for gk, t, c, hit in _owned_chunks(eg, G, tiles):
+            for gk, t, c in _owned_chunks(eg, G, tiles):
                 assert gk % G == eg and gk > last
                 last = gk
                 assert gk not in seen
                 seen[gk] = (t, c)
-                misses += (not hit)
         assert sorted(seen) == list(range(total_chunks))
-        # the manager numbers chunks tile after tile
-        k = 0
+        k = 0  # the manager numbers chunks tile after tile
         for t, _, nch in tiles:
             for c in range(nch):
                 assert seen[k] == (t, c)
                 k += 1
-        # a fetch-at-use only happens after a tile in which the group owned nothing
-        if all(n >= G for _, _, n in tiles):
-            assert misses == 0
+
+
+def test_constant_buffer_handshake_parities():
+    """const_full / const_empty (two stages): the manager loads tile ordinal i into stage i & 1 after waiting for the
+    ((i >> 1) - 1)-th completion of const_empty[i & 1]; the epilogue waits for completion (i >> 1) of const_full[i & 1]."""
+    for n_tiles in range(1, 9):
+        full = [0, 0]
+        empty = [0, 0]
+        loaded = []
+        for i in range(min(2, n_tiles)):
+            full[i & 1] += 1
+            loaded.append(i)
+        for it in range(n_tiles):          # epilogue consumes tile `it`, then the manager may load it + 2
+            assert it in loaded and full[it & 1] == (it >> 1) + 1
+            empty[it & 1] += 1
+            nxt = it + 2
+            if nxt < n_tiles:
+                assert empty[nxt & 1] >= (nxt >> 1)  # the completion the manager waits for has happened
+                full[nxt & 1] += 1
+                loaded.append(nxt)
