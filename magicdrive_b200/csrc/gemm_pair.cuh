@@ -363,11 +363,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // Column constants (bias, per-image shift, folded-LayerNorm column sums) of tile ordinal `itn` -> smC[itn & 1] by bulk
       // copies, a whole tile before the epilogue needs them: fetched by the epilogue warps themselves (even one chunk ahead)
       // they cost every chunk ~0.5 us of exposed L2 latency (chunk-level trace).
-      auto load_tile_consts = [&](int itn) {
+      // `block` = the epilogue is about to need them (never in steady state); otherwise the load is simply retried at the
+      // manager's next chunk, so that a slow warp at a tile boundary does not hold up the stores / box preparation of the rest.
+      int const_it = 0;  // next tile ordinal whose constants have to be fetched
+      auto load_tile_consts = [&](bool block) {
+        const int itn = const_it;
         const int t = cluster_id + itn * n_clusters;
         if (t >= total) return;
         const int as = itn & 1;
-        if (itn >= 2) mbar_wait(&const_empty[as], ((itn >> 1) - 1) & 1);  // the epilogue is done with tile itn - 2
+        if (itn >= 2) {  // the epilogue must be done with tile itn - 2
+          if (block) mbar_wait(&const_empty[as], ((itn >> 1) - 1) & 1);
+          else if (!mbar_test(&const_empty[as], ((itn >> 1) - 1) & 1)) return;
+        }
+        ++const_it;
         const int nt = t / pp.m_groups;
         const int mt = (t - nt * pp.m_groups) * CTAS + static_cast<int>(rank);
         const int img = min((mt / (p.tiles_w * p.tiles_h)) * p.bn, p.n_img - 1);
@@ -392,8 +400,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (p.rowbias) copy(dst + 1024, p.rowbias + static_cast<long long>(img) * p.rowbias_ld + n0);
         if (has_ln) copy(dst + 2048, pp.ln_colsum + n0);
       };
-      load_tile_consts(0);
-      load_tile_consts(1);
+      load_tile_consts(true);
+      load_tile_consts(true);
       int sto_it = 0;  // tile ordinal of the store cursor
       Cursor pre{cluster_id, 0, 0, 0, 0, 0, 0, 0, false}, sto{cluster_id, 0, 0, 0, 0, 0, 0, 0, false};
       enter_tile(pre);
@@ -412,16 +420,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int i = 0; i < Cfg::kAhead && pre.t < total; ++i) prepare();
       while (sto.t < total) {
         if (pre.t < total) prepare();
+        load_tile_consts(const_it <= sto_it);  // the chunk awaited below cannot be produced without its tile's constants
         const int buf = sto.k % NBUF;
         mbar_wait(&out_ready[buf], (sto.k / NBUF) & 1);
         if (sto.real) tma_store_4d(&tmOut, smO + buf * Cfg::kBufBytes, sto.col0 + sto.c * 32, sto.w0, sto.h0, sto.img0);
         bulk_commit_group();  // one group per chunk (empty for the phantom half of an odd pair) keeps the wait counts exact
         const int t_before = sto.t;
         advance(sto);
-        if (sto.t != t_before) {  // the last chunk of tile sto_it is on its way out: its constant buffer is about to be free
-          load_tile_consts(sto_it + 2);
-          ++sto_it;
-        }
+        if (sto.t != t_before) ++sto_it;
       }
       MDB_TRACE3(4);
       bulk_wait_group_all();
