@@ -341,21 +341,33 @@ class _Net:
                             pad=1, bias=b)
         return FMap(out, x.n, ho, wo, sp.c)
 
-    def encoder(self, x: FMap, temb_all, ctx_kv, lc):
+    def encoder(self, x: FMap, temb_all, ctx_kv, lc, on_skip=None):
+        """conv_in output -> (mid-block output, skip list).  `on_skip(i)` is called right after the kernels producing skip i
+        (and, with i = len(skips), the mid output) were enqueued: the pipeline records a CUDA event there."""
         skips = [x]
+
+        def mark():
+            if on_skip is not None:
+                on_skip(len(skips) - 1)
+
+        mark()
         for blk in self.down:
             for rs, tr in blk.layers:
                 x = self.resnet(rs, x, temb_all)
                 if tr is not None:
                     x = self.transformer(tr, x, ctx_kv, lc)
                 skips.append(x)
+                mark()
             if blk.sampler is not None:
                 x = self.downsample(blk.sampler, x)
                 skips.append(x)
+                mark()
         r0, tr, r1 = self.mid
         x = self.resnet(r0, x, temb_all)
         x = self.transformer(tr, x, ctx_kv, lc)
         x = self.resnet(r1, x, temb_all)
+        if on_skip is not None:
+            on_skip(len(skips))
         return x, skips
 
     CIN_PAD = 64  # latent channels are zero-padded to one 64-wide K block so conv_in runs on the tensor-core path
@@ -390,13 +402,15 @@ class UNetEngine(_Net):
         x, skips = self.forward_encoder(latents_pad, n, h, w, temb_all, ctx_kv, lc)
         return self.forward_decoder(x, skips, temb_all, ctx_kv, lc, down_res, mid_res)
 
-    def forward_encoder(self, latents_pad, n, h, w, temb_all, ctx_kv, lc):
+    def forward_encoder(self, latents_pad, n, h, w, temb_all, ctx_kv, lc, on_skip=None):
         """conv_in + down blocks + mid block: independent of the ControlNet residuals, so the pipeline runs it
         concurrently with the ControlNet on a second stream."""
         x = self.conv_in(latents_pad, n, h, w)
-        return self.encoder(x, temb_all, ctx_kv, lc)
+        return self.encoder(x, temb_all, ctx_kv, lc, on_skip=on_skip)
 
     def forward_decoder(self, x, skips, temb_all, ctx_kv, lc, down_res=None, mid_res=None) -> torch.Tensor:
+        """Up blocks + conv_out.  `skips` / `x` either are the encoder's own tensors with the ControlNet residuals passed in
+        `down_res` / `mid_res` (added here), or already carry them (ControlNetEngine.residuals(add_to=...)) with both None."""
         cfg = self.cfg
         skips = list(skips)
         if down_res is not None:
@@ -503,17 +517,35 @@ class ControlNetEngine(_Net):
                 conditioning_scale: float = 1.0, temb_all: Optional[torch.Tensor] = None):
         """latents [n*h*w, 64] bf16 channel-padded (n = scenes*views); t_f32 [n]; map_emb_per_view [n, h, w, 320] bf16.
         Returns (12 + 1 residual maps as [pixels, C] bf16 tensors)."""
+        x, skips = self.trunk(latents_pad, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view, temb_all)
+        down, mid = self.residuals(skips, x, conditioning_scale)
+        return down, mid, skips, x
+
+    def trunk(self, latents_pad, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view, temb_all=None):
+        """conv_in (+ BEV-map embedding) + down blocks + mid block of the ControlNet (unet_addon_rawbox.py:836-894)."""
         if temb_all is None:
             temb_all = self.time_embed(t_f32)
         x = self.conv_in(latents_pad, n, h, w, residual=map_emb_per_view)
-        x, skips = self.encoder(x, temb_all, ctx_kv, lc)
+        return self.encoder(x, temb_all, ctx_kv, lc)
+
+    def residuals(self, skips, x, conditioning_scale: float = 1.0, add_to=None, add_to_mid=None, before=None):
+        """The 12 + 1 zero convolutions (unet_addon_rawbox.py:898-915).  With `add_to` / `add_to_mid` (the UNet's own skip
+        tensors and mid output) every zero convolution takes that tensor as its epilogue residual and returns
+        `unet_skip + scale * zero_conv(controlnet_skip)`: the additions of unet_2d_condition_multiview.py:479-497 ride the
+        GEMM that produces the residual, which is then never written or re-read.  `before(i)` is called ahead of the
+        i-th launch (the pipeline waits there for the event of UNet skip i)."""
         down = []
         for i, s in enumerate(skips):
             wz, bz = self.W.conv(f"controlnet_down_blocks.{i}")
-            down.append(ops.linear(s.data, wz, bias=bz, out_scale=conditioning_scale))
+            if before is not None:
+                before(i)
+            down.append(ops.linear(s.data, wz, bias=bz, out_scale=conditioning_scale,
+                                   residual=None if add_to is None else add_to[i]))
         wz, bz = self.W.conv("controlnet_mid_block")
-        mid = ops.linear(x.data, wz, bias=bz, out_scale=conditioning_scale)
-        return down, mid, skips, x
+        if before is not None:
+            before(len(skips))
+        mid = ops.linear(x.data, wz, bias=bz, out_scale=conditioning_scale, residual=add_to_mid)
+        return down, mid
 
 
 class VaeDecoderEngine:

@@ -19,6 +19,7 @@ import os
 import torch
 
 from . import ops
+from .engine import FMap
 from .models import BEVControlNetModel, UNet2DConditionModelMultiview
 
 F32, BF16 = torch.float32, torch.bfloat16
@@ -155,6 +156,9 @@ class BEVControlNetDenoiser:
         # programmatic dependent launch on the single-stream UNet up path (A/B switch until measured: MDB_PDL_DECODER=1)
         self.pdl_decoder = os.environ.get("MDB_PDL_DECODER", "0") == "1"
         self.cfg_streams = cfg_streams
+        # ControlNet residual additions ride the zero convolutions' epilogues (MDB_FUSE_RESIDUAL_ADDS=0: the separate
+        # additions of round 1, kept as the A/B and as the path the sharded mode's halves use)
+        self.fuse_residual_adds = os.environ.get("MDB_FUSE_RESIDUAL_ADDS", "1") == "1"
         self.view_shard = view_shard
         unet.set_view_shard(view_shard)
         self._side = {}
@@ -273,6 +277,28 @@ class BEVControlNetDenoiser:
             main = torch.cuda.current_stream()
             side = self._side_stream(lat.device)
             side.wait_stream(main)
+            if self.fuse_residual_adds:
+                # The 13 zero convolutions take the UNet's own skip tensors as their epilogue residual (skip + scale * zero_conv):
+                # no separate additions, the ControlNet residuals are never written.  They run on the side stream behind the
+                # ControlNet trunk, each one waiting only for the event of the UNet skip it adds to.
+                with torch.cuda.stream(side), ops.workspace_slot(1):
+                    c_x, c_skips = ce.trunk(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["c_temb"])
+                ev = {}
+
+                def on_skip(i):
+                    ev[i] = torch.cuda.Event()
+                    ev[i].record(main)
+
+                xe, skips = ue.forward_encoder(x, V, h, w, st["u_temb"], st["u_kv"], st["lc"], on_skip=on_skip)
+                with torch.cuda.stream(side), ops.workspace_slot(1):
+                    down, mid = ce.residuals(c_skips, c_x, st["cond_scale"], add_to=[s.data for s in skips], add_to_mid=xe.data,
+                                             before=lambda i: side.wait_event(ev[i]))
+                main.wait_stream(side)
+                skips = [FMap(d, s.n, s.h, s.w, s.c) for d, s in zip(down, skips)]
+                xe = FMap(mid, xe.n, xe.h, xe.w, xe.c)
+                with ops.pdl_region(self.pdl_decoder):
+                    eps = ue.forward_decoder(xe, skips, st["u_temb"], st["u_kv"], st["lc"])
+                return eps
             with torch.cuda.stream(side), ops.workspace_slot(1):
                 down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
                                              temb_all=st["c_temb"])
@@ -281,6 +307,12 @@ class BEVControlNetDenoiser:
             # single stream from here on: the next kernel's launch + prologue may overlap its predecessor's tail
             with ops.pdl_region(self.pdl_decoder):
                 eps = ue.forward_decoder(xe, skips, st["u_temb"], st["u_kv"], st["lc"], down, mid)
+        elif self.fuse_residual_adds and st.get("u_temb") is not None:
+            c_x, c_skips = ce.trunk(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st.get("c_temb"))
+            xe, skips = ue.forward_encoder(x, V, h, w, st["u_temb"], st["u_kv"], st["lc"])
+            down, mid = ce.residuals(c_skips, c_x, st["cond_scale"], add_to=[s.data for s in skips], add_to_mid=xe.data)
+            skips = [FMap(d, s.n, s.h, s.w, s.c) for d, s in zip(down, skips)]
+            eps = ue.forward_decoder(FMap(mid, xe.n, xe.h, xe.w, xe.c), skips, st["u_temb"], st["u_kv"], st["lc"])
         else:
             down, mid, _, _ = ce.forward(x, V, h, w, st["t_dev"], st["c_kv"], st["lc"], st["map"], st["cond_scale"],
                                          temb_all=st.get("c_temb"))

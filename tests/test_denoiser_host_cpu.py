@@ -77,7 +77,9 @@ def _denoiser(seed, scheduler):
     cn = models.BEVControlNetModel(**asdict(ccfg))
     un.load_state_dict(usd)
     cn.load_state_dict(csd)
-    return BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, scheduler=scheduler)
+    pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, scheduler=scheduler)
+    pipe.fuse_residual_adds = False  # the stand-in engines only restate whole forwards (the fused path: test_engine_host_cpu.py)
+    return pipe
 
 
 def _call(pipe, inp, steps, guidance, **kw):
@@ -136,6 +138,7 @@ def test_unconditional_map_options_reproduce_the_reference(cpu_standins, case):
         csd = dict(csd, uncond_map=cn.uncond_map.clone())
     cn.load_state_dict(csd)
     pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False)
+    pipe.fuse_residual_adds = False  # stand-in engines restate whole forwards only
     opts = dict(use_zero_map_as_unconditional=(case == "zero_map"), bbox_max_length=9 if case == "max_len9" else None)
     out = _call(pipe, inp, p["steps"], p["guidance"], **opts)
     ref = p["outputs"][case]

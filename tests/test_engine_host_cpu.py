@@ -124,12 +124,16 @@ def test_layernorm_fold_rounding_is_bf16_weight_noise(monkeypatch):
 
 
 @torch.no_grad()
-@pytest.mark.parametrize("scheduler,guidance", [("ddim", 2.0), ("unipc", 2.0), ("ddim", 1.0)])
-def test_denoiser_through_emulated_operators_matches_the_oracle_loop(emulated, scheduler, guidance):
+@pytest.mark.parametrize("scheduler,guidance,fused", [("ddim", 2.0, True), ("unipc", 2.0, True), ("ddim", 1.0, True),
+                                                      ("ddim", 2.0, False)])
+def test_denoiser_through_emulated_operators_matches_the_oracle_loop(emulated, scheduler, guidance, fused):
+    """fused: the ControlNet residual additions (unet_2d_condition_multiview.py:479-497) ride the zero convolutions' epilogues
+    (ControlNetEngine.residuals(add_to=...)); not fused: the separate additions of UNetEngine.forward_decoder."""
     ucfg, ccfg = tiny_configs()
     un, cn, usd, csd = _modules(ucfg, ccfg, 41)
     inp = synthetic_inputs(2, 6, 10, 13, n_box=3, map_hw=52, seed=9)
     pipe = BEVControlNetDenoiser(un, cn, use_cuda_graph=False, overlap_controlnet=False, scheduler=scheduler)
+    pipe.fuse_residual_adds = fused
     out = pipe(image=inp["bev_map"], camera_param=inp["camera_param"], prompt_embeds=inp["prompt_embeds"],
                negative_prompt_embeds=inp["negative_prompt_embeds"], latents=inp["latents"], num_inference_steps=3,
                guidance_scale=guidance, bev_controlnet_kwargs={"bboxes_3d_data": inp["bboxes_3d_data"]})
