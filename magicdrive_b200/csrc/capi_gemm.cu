@@ -101,8 +101,9 @@ int validate(const mdb_gemm_desc* d) {
   if ((reinterpret_cast<uintptr_t>(d->a0) | reinterpret_cast<uintptr_t>(d->a1) | reinterpret_cast<uintptr_t>(d->w) |
        reinterpret_cast<uintptr_t>(d->out) | reinterpret_cast<uintptr_t>(d->residual)) & 15)
     return set_error(MDB_ERR_INVALID, "mdb_gemm_conv: pointers must be 16-byte aligned");
-  if (d->epi_mode == 1 && (d->n_out % 256 || d->residual || d->rowbias || d->out_is_f32))
-    return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: GEGLU epilogue needs n_out %% 256 == 0 and a plain bf16 output");
+  if (d->epi_mode == 1 && (d->n_out % 256 || d->residual || d->rowbias || d->out_is_f32 || d->stats_out))
+    return set_error(MDB_ERR_UNSUPPORTED, "mdb_gemm_conv: GEGLU epilogue needs n_out %% 256 == 0 and a plain bf16 output "
+                                          "(no residual, per-image shift or row statistics)");
   return MDB_OK;
 }
 

@@ -120,6 +120,12 @@ __device__ __forceinline__ unsigned long long gelu_erf2(unsigned long long x2) {
   return fma2(hx2, pk2(copysignf(r0, x0), copysignf(r1, x1)), hx2);
 }
 
+// compile-time epilogue options of one instantiation of the tile loop (selected once per kernel by a warp-uniform switch)
+template <bool LN_, bool RES_, bool STATS_, bool ROWB_, bool SCALED_, bool GEGLU_>
+struct EpiFlags {
+  static constexpr bool LN = LN_, RES = RES_, STATS = STATS_, ROWB = ROWB_, SCALED = SCALED_, GEGLU = GEGLU_;
+};
+
 template <int BLOCK_N, int CTAS>
 struct PairCfg {
   static constexpr int kBRows = BLOCK_N / CTAS;
@@ -223,6 +229,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&out_ready[i], 4);  // the four lane-quarter warps that own a chunk
     }
     fence_barrier_init();
+    MDB_TRACE3(11);
   }
   if (warp == 2) {
     if constexpr (PAIR) {
@@ -232,10 +239,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tmem_alloc(tmem_slot, Cfg::kTmemCols);
       tmem_relinquish();
     }
+    if (lane == 0) MDB_TRACE3(12);
   }
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) MDB_TRACE3(13);
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above overlapped the predecessor's tail; from here on its results are complete and visible.  The
   // dependent grid may be scheduled as soon as every CTA of this one holds its shared memory and TMEM.
@@ -302,6 +311,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (lane == 0 && it == 0 && i == 0) MDB_TRACE3(14);
           if (elect_one()) {
             const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smA + stage * kABytes));
             const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smB + stage * Cfg::kBBytes));
@@ -439,6 +449,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // G groups of four warps (one per TMEM lane quarter); the 32-column chunks go round-robin to the groups.  All
     // arithmetic on fp32 PAIRS (FFMA2 / FADD2 / FMUL2): out = A_row * acc + (B_row * colsum_n + bias_n) [+ residual] with
     // A_row = rstd * scale, B_row = -mean * rstd * scale (folded LayerNorm) or A_row = scale, B_row = 0.
+    //
+    // The tile loop is instantiated once per combination of epilogue options (EpiFlags) and selected by one warp-uniform
+    // switch: with the options as run-time flags every 32-column chunk issued ~400 instructions, 167 of them predicated off
+    // (ncu source page of the K = 320 token GEMMs, profiles/ncu_gemm_pair_r2_s14.summary.txt), and a chunk took a warp
+    // ~0.9 us -- three chunks per tile against 0.8 us of MMA.
     constexpr int G = Cfg::kEpiGroups;
     const int q = warp & 3;
     const int eg = (warp - 3) >> 2;
@@ -450,8 +465,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int lw = rem - lh * p.bw;
     const uint32_t my_row = smem_u32(smO) + row * 64;  // this thread's 64-byte row inside a staging box (shared-space address)
     const int swz = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk j sits at j ^ swz
-    const bool has_ln = pp.ln_stats != nullptr;
     const float scale = p.out_scale;
+    const bool has_bias = p.bias != nullptr;
     // Where this thread's accumulator row lands for tile t: one decomposition per tile (multiply-high by host-computed
     // reciprocals, no integer division), carried from the prefetch of the previous iteration.
     struct TileRow {
@@ -476,36 +491,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       r.img_tile = min(tn * p.bn, p.n_img - 1);
       return r;
     };
-    constexpr int PF = (G <= 2) ? 8 : 4;  // LayerNorm row-statistics partials fetched one tile ahead (the rest, if any, at use)
-    float2 pf[PF];
-    auto fetch_stats = [&](const TileRow& r) {
-#pragma unroll
-      for (int j = 0; j < PF; ++j) pf[j] = make_float2(0.f, 0.f);
-      if (has_ln && r.ok) {
-        const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + static_cast<long long>(r.pix) * pp.ln_parts;
-#pragma unroll
-        for (int j = 0; j < PF; ++j)
-          if (j < pp.ln_parts) pf[j] = __ldg(sp + j);
-      }
-    };
-    // Column constants of a tile sit in smC[as] (bulk-copied by the manager one tile ahead): broadcast LDS.128 reads.
-    // t0/t1 = (bias + shift) * scale [+ B_row * colsum] for columns col .. col + 3 of the tile.
-    constexpr int HALFN = BLOCK_N / 2;
-    const bool has_rowb = p.rowbias != nullptr, has_bias = p.bias != nullptr;
-    auto col_consts = [&](uint32_t cst, int col, unsigned long long B2, unsigned long long& t0, unsigned long long& t1) {
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_bias) b = lds_f4(cst + col * 4);
-      if (has_rowb) {
-        const float4 r = lds_f4(cst + 1024 + col * 4);
-        b.x += r.x, b.y += r.y, b.z += r.z, b.w += r.w;
-      }
-      t0 = pk2(b.x, b.y), t1 = pk2(b.z, b.w);
-      if (scale != 1.f) t0 = mul2(t0, pk2(scale, scale)), t1 = mul2(t1, pk2(scale, scale));
-      if (has_ln) {
-        const float4 cs = lds_f4(cst + 2048 + col * 4);
-        t0 = fma2(B2, pk2(cs.x, cs.y), t0), t1 = fma2(B2, pk2(cs.z, cs.w), t1);
-      }
-    };
     // first chunk of tile (t, gk0 = running chunk number at its start) owned by this group, or -1
     auto first_owned = [&](int gk0, int nch) {
       const int c = ((eg - gk0) % G + G) % G;
@@ -515,143 +500,209 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int left = (pp.out_cols - r.nt * out_per_tile) / 32;
       return left < ch_tile ? left : ch_tile;
     };
-    TileRow cur = locate(cluster_id);
-    fetch_stats(cur);
-    int it = 0;
-    int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
-    for (int t = cluster_id; t < total; t += n_clusters, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      // this tile's row scalars from the prefetched statistics
-      float rowA = scale, rowB = 0.f;
-      if (has_ln) {
-        float s = 0.f, ss = 0.f;
+    constexpr int PF = (G <= 2) ? 8 : 4;  // LayerNorm row-statistics partials fetched one tile ahead (the rest, if any, at use)
+    constexpr int HALFN = BLOCK_N / 2;
+
+    auto epi_loop = [&](auto flags) {
+      using F = decltype(flags);
+      constexpr bool LN = F::LN, RES = F::RES, STATS = F::STATS, ROWB = F::ROWB, SCALED = F::SCALED, GLU = F::GEGLU;
+      float2 pf[PF];
+      auto fetch_stats = [&](const TileRow& r) {
+        if constexpr (LN) {
 #pragma unroll
-        for (int j = 0; j < PF; ++j) s += pf[j].x, ss += pf[j].y;
-        if (cur.ok) {
-          const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + static_cast<long long>(cur.pix) * pp.ln_parts;
-          for (int j = PF; j < pp.ln_parts; ++j) {
-            const float2 v = __ldg(sp + j);
-            s += v.x, ss += v.y;
+          for (int j = 0; j < PF; ++j) pf[j] = make_float2(0.f, 0.f);
+          if (r.ok) {
+            const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + static_cast<long long>(r.pix) * pp.ln_parts;
+#pragma unroll
+            for (int j = 0; j < PF; ++j)
+              if (j < pp.ln_parts) pf[j] = __ldg(sp + j);
           }
         }
-        const float mean = s * pp.ln_inv_c;
-        const float rstd = rsqrtf(fmaxf(ss * pp.ln_inv_c - mean * mean, 0.f) + pp.ln_eps);
-        rowA = rstd * scale;
-        rowB = -mean * rowA;
-      }
-      // next tile's position / statistics: loads in flight while this tile is processed
-      const TileRow nxt = locate(t + n_clusters);
-      fetch_stats(nxt);
-      const int nch = chunks_of(cur);
-      const int gk_tile = gk;  // running chunk number of this tile's chunk 0
-      const unsigned long long A2 = pk2(rowA, rowA), B2 = pk2(rowB, rowB);
-      unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
-      const uint32_t cst = smem_u32(smC) + as * Cfg::kConstStage;
-      mbar_wait(&const_full[as], aphase);  // landed a tile ago
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
-      const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      int tslot = (warp == 3 && lane == 0 && it < 2) ? 16 + it * 20 : -1;  // [acc_full | (box ready, acc read, stored, arrived) x <= 4]
-      if (tslot >= 0) {
-        MDB_TRACE3(tslot);
-        ++tslot;
-      }
-      const int tslot_end = tslot + 16;
+      };
+      // Column constants of a tile sit in smC[as] (bulk-copied by the manager one tile ahead): broadcast LDS.128 reads.
+      // t0/t1 = (bias + shift) * scale [+ B_row * colsum] for columns col .. col + 3 of the tile.
+      auto col_consts = [&](uint32_t cst, int col, unsigned long long B2, unsigned long long& t0, unsigned long long& t1) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias) b = lds_f4(cst + col * 4);
+        if constexpr (ROWB) {
+          const float4 r = lds_f4(cst + 1024 + col * 4);
+          b.x += r.x, b.y += r.y, b.z += r.z, b.w += r.w;
+        }
+        t0 = pk2(b.x, b.y), t1 = pk2(b.z, b.w);
+        if constexpr (SCALED) t0 = mul2(t0, pk2(scale, scale)), t1 = mul2(t1, pk2(scale, scale));
+        if constexpr (LN) {
+          const float4 cs = lds_f4(cst + 2048 + col * 4);
+          t0 = fma2(B2, pk2(cs.x, cs.y), t0), t1 = fma2(B2, pk2(cs.z, cs.w), t1);
+        }
+      };
+      TileRow cur = locate(cluster_id);
+      fetch_stats(cur);
+      int it = 0;
+      int gk = 0;  // running chunk number (same sequence as the staging-buffer manager's cursors)
+      for (int t = cluster_id; t < total; t += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        // this tile's row scalars from the prefetched statistics
+        float rowA = scale, rowB = 0.f;
+        if constexpr (LN) {
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < PF; ++j) s += pf[j].x, ss += pf[j].y;
+          if (cur.ok) {
+            const float2* sp = reinterpret_cast<const float2*>(pp.ln_stats) + static_cast<long long>(cur.pix) * pp.ln_parts;
+            for (int j = PF; j < pp.ln_parts; ++j) {
+              const float2 v = __ldg(sp + j);
+              s += v.x, ss += v.y;
+            }
+          }
+          const float mean = s * pp.ln_inv_c;
+          const float rstd = rsqrtf(fmaxf(ss * pp.ln_inv_c - mean * mean, 0.f) + pp.ln_eps);
+          rowA = rstd * scale;
+          rowB = -mean * rowA;
+        }
+        // next tile's position / statistics: loads in flight while this tile is processed
+        const TileRow nxt = locate(t + n_clusters);
+        fetch_stats(nxt);
+        const int nch = chunks_of(cur);
+        const int gk_tile = gk;  // running chunk number of this tile's chunk 0
+        const unsigned long long A2 = pk2(rowA, rowA), B2 = pk2(rowB, rowB);
+        unsigned long long st_s2 = pk2(0.f, 0.f), st_ss2 = pk2(0.f, 0.f);
+        const uint32_t cst = smem_u32(smC) + as * Cfg::kConstStage;
+        mbar_wait(&const_full[as], aphase);  // landed a tile ago
+        mbar_wait(&acc_full[as], aphase);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#ifdef MDB_TRACE_CHUNKS  // chunk-level stamps of the first epilogue warp (debug builds only: tools/build_variant.sh -DMDB_TRACE_CHUNKS)
+        int tslot = (warp == 3 && lane == 0 && it < 2) ? 16 + it * 20 : -1;  // [acc_full | (box ready, acc read, stored, arrived) x <= 4]
+        if (tslot >= 0) {
+          MDB_TRACE3(tslot);
+          ++tslot;
+        }
+        const int tslot_end = tslot + 16;
 #define MDB_TRACE_CHUNK() do { if (tslot >= 0 && tslot < tslot_end) { MDB_TRACE3(tslot); ++tslot; } } while (0)
+#else
+#define MDB_TRACE_CHUNK() do { } while (0)
+#endif
 
-      // the chunks go round-robin over the running chunk number to the groups: balanced even when a tile has 5 chunks
-      for (int c = first_owned(gk_tile, nch); c >= 0 && c < nch; c += G) {
-        gk = gk_tile + c;
-        const int buf = gk % NBUF;
-        const uint32_t srow = my_row + buf * Cfg::kBufBytes;
-        if (!geglu) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while the constants are combined and the staging box is awaited
-          unsigned long long pre[16];
+        // the chunks go round-robin over the running chunk number to the groups: balanced even when a tile has 5 chunks
+        for (int c = first_owned(gk_tile, nch); c >= 0 && c < nch; c += G) {
+          gk = gk_tile + c;
+          const int buf = gk % NBUF;
+          const uint32_t srow = my_row + buf * Cfg::kBufBytes;
+          if constexpr (!GLU) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_addr + c * 32, v);  // in flight while the constants are combined and the staging box is awaited
+            unsigned long long pre[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) col_consts(cst, c * 32 + 4 * j, B2, pre[2 * j], pre[2 * j + 1]);
-          mbar_wait(&res_full[buf], (gk / NBUF) & 1);
-          MDB_TRACE_CHUNK();
-          uint4 r[4];
-          if (pp.use_res_tma) {
+            for (int j = 0; j < 8; ++j) col_consts(cst, c * 32 + 4 * j, B2, pre[2 * j], pre[2 * j + 1]);
+            mbar_wait(&res_full[buf], (gk / NBUF) & 1);
+            MDB_TRACE_CHUNK();
+            uint4 r[4];
+            if constexpr (RES) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) r[j] = lds_u4(srow + ((j ^ swz) << 4));
-          }
-          tmem_ld_wait();
-          MDB_TRACE_CHUNK();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), pre[4 * j]);
-            unsigned long long o1 = fma2(A2, pk2u(v[8 * j + 2], v[8 * j + 3]), pre[4 * j + 1]);
-            unsigned long long o2 = fma2(A2, pk2u(v[8 * j + 4], v[8 * j + 5]), pre[4 * j + 2]);
-            unsigned long long o3 = fma2(A2, pk2u(v[8 * j + 6], v[8 * j + 7]), pre[4 * j + 3]);
-            if (pp.use_res_tma) {
-              o0 = add2(o0, bf2_to_f2(r[j].x)), o1 = add2(o1, bf2_to_f2(r[j].y));
-              o2 = add2(o2, bf2_to_f2(r[j].z)), o3 = add2(o3, bf2_to_f2(r[j].w));
-            }
-            if (pp.stats_out) {
-              st_s2 = add2(add2(st_s2, add2(o0, o1)), add2(o2, o3));
-              st_ss2 = fma2(o0, o0, fma2(o1, o1, fma2(o2, o2, fma2(o3, o3, st_ss2))));
-            }
-            sts_u4(srow + ((j ^ swz) << 4), make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3)));
-          }
-        } else {
-          constexpr int HALF = BLOCK_N / 2;
-          mbar_wait(&res_full[buf], (gk / NBUF) & 1);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[16], g[16];
-            tmem_ld_32x16(lane_addr + c * 32 + hh * 16, v);
-            tmem_ld_32x16(lane_addr + HALF + c * 32 + hh * 16, g);
-            unsigned long long tv[8], tg[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              col_consts(cst, c * 32 + hh * 16 + 4 * j, B2, tv[2 * j], tv[2 * j + 1]);
-              col_consts(cst, HALFN + c * 32 + hh * 16 + 4 * j, B2, tg[2 * j], tg[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) r[j] = lds_u4(srow + ((j ^ swz) << 4));
             }
             tmem_ld_wait();
+            MDB_TRACE_CHUNK();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              unsigned long long o[4];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int k = 8 * j + 4 * e;
-                const unsigned long long a0 = fma2(A2, pk2u(v[k], v[k + 1]), tv[k / 2]), a1 = fma2(A2, pk2u(v[k + 2], v[k + 3]), tv[k / 2 + 1]);
-                const unsigned long long g0 = fma2(A2, pk2u(g[k], g[k + 1]), tg[k / 2]), g1 = fma2(A2, pk2u(g[k + 2], g[k + 3]), tg[k / 2 + 1]);
-                o[2 * e] = mul2(a0, gelu_erf2(g0));
-                o[2 * e + 1] = mul2(a1, gelu_erf2(g1));
+            for (int j = 0; j < 4; ++j) {
+              unsigned long long o0 = fma2(A2, pk2u(v[8 * j], v[8 * j + 1]), pre[4 * j]);
+              unsigned long long o1 = fma2(A2, pk2u(v[8 * j + 2], v[8 * j + 3]), pre[4 * j + 1]);
+              unsigned long long o2 = fma2(A2, pk2u(v[8 * j + 4], v[8 * j + 5]), pre[4 * j + 2]);
+              unsigned long long o3 = fma2(A2, pk2u(v[8 * j + 6], v[8 * j + 7]), pre[4 * j + 3]);
+              if constexpr (RES) {
+                o0 = add2(o0, bf2_to_f2(r[j].x)), o1 = add2(o1, bf2_to_f2(r[j].y));
+                o2 = add2(o2, bf2_to_f2(r[j].z)), o3 = add2(o3, bf2_to_f2(r[j].w));
               }
-              sts_u4(srow + (((hh * 2 + j) ^ swz) << 4), make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3])));
+              if constexpr (STATS) {
+                st_s2 = add2(add2(st_s2, add2(o0, o1)), add2(o2, o3));
+                st_ss2 = fma2(o0, o0, fma2(o1, o1, fma2(o2, o2, fma2(o3, o3, st_ss2))));
+              }
+              sts_u4(srow + ((j ^ swz) << 4), make_uint4(f2_to_bf2(o0), f2_to_bf2(o1), f2_to_bf2(o2), f2_to_bf2(o3)));
+            }
+            MDB_TRACE_CHUNK();
+          } else {
+            constexpr int HALF = BLOCK_N / 2;
+            mbar_wait(&res_full[buf], (gk / NBUF) & 1);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16], g[16];
+              tmem_ld_32x16(lane_addr + c * 32 + hh * 16, v);
+              tmem_ld_32x16(lane_addr + HALF + c * 32 + hh * 16, g);
+              unsigned long long tv[8], tg[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                col_consts(cst, c * 32 + hh * 16 + 4 * j, B2, tv[2 * j], tv[2 * j + 1]);
+                col_consts(cst, HALFN + c * 32 + hh * 16 + 4 * j, B2, tg[2 * j], tg[2 * j + 1]);
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                unsigned long long o[4];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int k = 8 * j + 4 * e;
+                  const unsigned long long a0 = fma2(A2, pk2u(v[k], v[k + 1]), tv[k / 2]), a1 = fma2(A2, pk2u(v[k + 2], v[k + 3]), tv[k / 2 + 1]);
+                  const unsigned long long g0 = fma2(A2, pk2u(g[k], g[k + 1]), tg[k / 2]), g1 = fma2(A2, pk2u(g[k + 2], g[k + 3]), tg[k / 2 + 1]);
+                  o[2 * e] = mul2(a0, gelu_erf2(g0));
+                  o[2 * e + 1] = mul2(a1, gelu_erf2(g1));
+                }
+                sts_u4(srow + (((hh * 2 + j) ^ swz) << 4), make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3])));
+              }
             }
           }
+          fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_ready[buf]);
+          if constexpr (!GLU) MDB_TRACE_CHUNK();
         }
-        if (!geglu) MDB_TRACE_CHUNK();
-        fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&out_ready[buf]);
-        if (!geglu) MDB_TRACE_CHUNK();
-      }
 #undef MDB_TRACE_CHUNK
-      gk = gk_tile + nch;
-      if (pp.stats_out && cur.ok) {
-        float s0, s1, q0, q1;
-        upk2(st_s2, s0, s1);
-        upk2(st_ss2, q0, q1);
-        // one slot per (N tile, epilogue group): [pix][n_tiles][G]
-        reinterpret_cast<float2*>(pp.stats_out)[(static_cast<long long>(cur.pix) * pp.n_tiles + cur.nt) * G + eg] =
-            make_float2(s0 + s1, q0 + q1);
+        gk = gk_tile + nch;
+        if constexpr (STATS) {
+          if (cur.ok) {
+            float s0, s1, q0, q1;
+            upk2(st_s2, s0, s1);
+            upk2(st_ss2, q0, q1);
+            // one slot per (N tile, epilogue group): [pix][n_tiles][G]
+            reinterpret_cast<float2*>(pp.stats_out)[(static_cast<long long>(cur.pix) * pp.n_tiles + cur.nt) * G + eg] =
+                make_float2(s0 + s1, q0 + q1);
+          }
+        }
+        // release this accumulator stage to the MMA warp of the leader CTA, and the constants' buffer to the manager
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
+          else mbar_arrive(&acc_empty[as]);
+          mbar_arrive(&const_empty[as]);
+        }
+        cur = nxt;
+        if (warp == 3 && lane == 0 && it == 0) MDB_TRACE3(8);
       }
-      // release this accumulator stage to the MMA warp of the leader CTA, and the constants' buffer to the manager
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
-        else mbar_arrive(&acc_empty[as]);
-        mbar_arrive(&const_empty[as]);
+    };
+    // one warp-uniform selection of the loop's instantiation (GEGLU tiles take no residual / per-image shift and emit no
+    // statistics: host check)
+    const int code = (pp.ln_stats != nullptr ? 1 : 0) | (pp.use_res_tma ? 2 : 0) | (pp.stats_out != nullptr ? 4 : 0) |
+                     (p.rowbias != nullptr ? 8 : 0) | (scale != 1.f ? 16 : 0);
+    if (geglu) {
+      switch (code & 17) {
+        case 0: epi_loop(EpiFlags<false, false, false, false, false, true>{}); break;
+        case 1: epi_loop(EpiFlags<true, false, false, false, false, true>{}); break;
+        case 16: epi_loop(EpiFlags<false, false, false, false, true, true>{}); break;
+        default: epi_loop(EpiFlags<true, false, false, false, true, true>{}); break;
       }
-      cur = nxt;
-      if (warp == 3 && lane == 0 && it == 0) MDB_TRACE3(8);
+    } else {
+      switch (code) {
+#define MDB_EPI_CASE(n) \
+  case n: epi_loop(EpiFlags<((n) & 1) != 0, ((n) & 2) != 0, ((n) & 4) != 0, ((n) & 8) != 0, ((n) & 16) != 0, false>{}); break;
+        MDB_EPI_CASE(0) MDB_EPI_CASE(1) MDB_EPI_CASE(2) MDB_EPI_CASE(3) MDB_EPI_CASE(4) MDB_EPI_CASE(5) MDB_EPI_CASE(6) MDB_EPI_CASE(7)
+        MDB_EPI_CASE(8) MDB_EPI_CASE(9) MDB_EPI_CASE(10) MDB_EPI_CASE(11) MDB_EPI_CASE(12) MDB_EPI_CASE(13) MDB_EPI_CASE(14)
+        MDB_EPI_CASE(15) MDB_EPI_CASE(16) MDB_EPI_CASE(17) MDB_EPI_CASE(18) MDB_EPI_CASE(19) MDB_EPI_CASE(20) MDB_EPI_CASE(21)
+        MDB_EPI_CASE(22) MDB_EPI_CASE(23) MDB_EPI_CASE(24) MDB_EPI_CASE(25) MDB_EPI_CASE(26) MDB_EPI_CASE(27) MDB_EPI_CASE(28)
+        MDB_EPI_CASE(29) MDB_EPI_CASE(30)
+        default: epi_loop(EpiFlags<true, true, true, true, true, false>{}); break;
+#undef MDB_EPI_CASE
+      }
     }
     if (warp == 3 && lane == 0) MDB_TRACE3(6);
   }

@@ -131,16 +131,17 @@ class _Weights:
             self.t[name + ".w"], self.t[name + ".c"], self.t[name + ".cs"] = wg.contiguous(), _f32(c), _f32(cs)
         return self.t[name + ".w"], self.t[name + ".c"], self.t[name + ".cs"]
 
-    def folded_connector(self, blk):
-        """W' = Wc @ Wo, b' = 2 Wc b_o + b_c  (fp32 fold, bf16 storage)."""
-        k = blk + ".attn4.fold"
+    def folded_connector(self, blk, bias_count: int = 2):
+        """W' = Wc @ Wo, b' = bias_count * Wc b_o + b_c  (fp32 fold, bf16 storage).  bias_count = attention outputs summed
+        before the connector: 2 in 'add' mode (one per neighbour, blocks.py:213-218), 1 in 'concat' / 'self' mode."""
+        k = blk + f".attn4.fold{bias_count}"
         if k + ".w" not in self.t:
             wo = self.raw(blk + ".attn4.to_out.0.weight").float()
             bo = self.raw(blk + ".attn4.to_out.0.bias").float()
             wc = self.raw(blk + ".connector.weight").float()
             bc = self.raw(blk + ".connector.bias").float()
             self.t[k + ".w"] = _bf(wc @ wo)
-            self.t[k + ".b"] = _f32(2.0 * (wc @ bo) + bc)
+            self.t[k + ".b"] = _f32(float(bias_count) * (wc @ bo) + bc)
         return self.t[k + ".w"], self.t[k + ".b"]
 
 
@@ -302,10 +303,34 @@ class _Net:
         X, sx = ops.linear(o, wo, bias=bo, residual=X, emit_stats=True)
         # --- cross-view attention
         if tr.multiview:
-            if cfg.neighboring_attn_type != "add" or cfg.zero_module_type != "zero_linear":
-                raise NotImplementedError("only neighboring_attn_type='add' with the zero_linear connector (the shipped "
-                                          "configs/model/SDv1.5mv_rawbox.yaml:19-20) is implemented")
-            if not self._sharded():
+            at = cfg.neighboring_attn_type
+            if at not in ("add", "concat", "self") or cfg.zero_module_type != "zero_linear":
+                raise NotImplementedError("neighboring_attn_type must be 'add' / 'concat' / 'self' and the connector zero_linear "
+                                          "(blocks.py:74-89; the shipped configs/model/SDv1.5mv_rawbox.yaml:19-20 uses add + zero_linear)")
+            if self._sharded() and at != "add":
+                raise NotImplementedError("views split across GPUs: only neighboring_attn_type='add' is implemented")
+            if at == "self":
+                # blocks.py:134-138, 209-211: one attention over the tokens of ALL views of a scene.  The token matrix is
+                # scene-major then view-major, so this is the self-attention kernel with batch = scenes and n_cam * L tokens.
+                n_cam = len(cfg.neighboring_view_pair)
+                wqkv, cq, sq = W.ln_lin(blk + ".attn4.lnqkv", blk + ".norm4",
+                                        [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
+                qkv = ops.linear(X, wqkv, bias=cq, ln=sx, ln_colsum=sq)
+                o = ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], b=V // n_cam, heads=heads, lq=n_cam * L, lk=n_cam * L, d=d,
+                                  ldq=3 * C, ldk=3 * C, ldv=3 * C, scale=scale)
+            elif at == "concat":
+                # blocks.py:122-133: ONE softmax over the keys of both neighbours.  Their K/V rows are gathered into one
+                # [V, n_nb * L, 2C] buffer (a device copy; this non-default mode is not on the benchmarked path)
+                wq, cq, sq = W.ln_lin(blk + ".attn4.lnq", blk + ".norm4", [blk + ".attn4.to_q"])
+                wkv, ckv, skv = W.ln_lin(blk + ".attn4.lnkv", blk + ".norm4", [blk + ".attn4.to_k", blk + ".attn4.to_v"])
+                q = ops.linear(X, wq, bias=cq, ln=sx, ln_colsum=sq)
+                kv = ops.linear(X, wkv, bias=ckv, ln=sx, ln_colsum=skv)
+                idx = self.kv_index(V)
+                n_nb = idx.shape[1]
+                kvc = kv.view(V, L, 2 * C)[idx.long()].reshape(V * n_nb * L, 2 * C)
+                o = ops.attention(q, kvc, kvc[:, C:], b=V, heads=heads, lq=L, lk=n_nb * L, d=d, ldq=C, ldk=2 * C, ldv=2 * C,
+                                  scale=scale)
+            elif not self._sharded():
                 wqkv, cq, sq = W.ln_lin(blk + ".attn4.lnqkv", blk + ".norm4",
                                         [blk + ".attn4.to_q", blk + ".attn4.to_k", blk + ".attn4.to_v"])
                 qkv = ops.linear(X, wqkv, bias=cq, ln=sx, ln_colsum=sq)
@@ -323,7 +348,7 @@ class _Net:
                 self.view_shard.half_group.barrier(0)
                 o = ops.attention_multi(q, [(t, t[:, C:], 2 * C, vg) for t, vg in srcs], b=V, heads=heads, lq=L, lk=L, d=d,
                                         ldq=C, scale=scale, kv_index=self.kv_index(V), n_sets=2)
-            wf, bf_ = W.folded_connector(blk)
+            wf, bf_ = W.folded_connector(blk, bias_count=2 if at == "add" else 1)
             X, sx = ops.linear(o, wf, bias=bf_, residual=X, emit_stats=True)
         # --- GEGLU feed-forward
         wg, cg, sg = W.ln_lin(blk + ".ff.lnproj", blk + ".norm3", [blk + ".ff.net.0.proj"], geglu=True)

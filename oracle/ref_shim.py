@@ -101,7 +101,8 @@ def build_reference_models(ucfg, ccfg, img_size=(224, 400), **controlnet_kwargs)
         cross_attention_dim=ucfg.cross_attention_dim, attention_head_dim=ucfg.attention_head_dim,
         norm_num_groups=ucfg.norm_num_groups)
     mv = R.UNet2DConditionModelMultiview.from_unet_2d_condition(
-        base, neighboring_view_pair=dict(ucfg.neighboring_view_pair), img_size=list(img_size))
+        base, neighboring_view_pair=dict(ucfg.neighboring_view_pair), img_size=list(img_size),
+        neighboring_attn_type=ucfg.neighboring_attn_type)
     cn = R.BEVControlNetModel.from_unet(
         base, map_size=list(ccfg.map_size),
         conditioning_embedding_out_channels=list(ccfg.conditioning_embedding_out_channels),

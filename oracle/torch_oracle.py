@@ -106,9 +106,9 @@ def _ln(sd, p, x):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
 
 
-def transformer_block(sd: SD, p: str, x, ctx, heads, multiview: bool, neighbors=None):
+def transformer_block(sd: SD, p: str, x, ctx, heads, multiview: bool, neighbors=None, attn_type: str = "add"):
     """BasicTransformerBlock.forward (attention.py:123-182) / BasicMultiviewTransformerBlock.forward
-    (magicdrive/networks/blocks.py:144-238, 'add' mode of _construct_attn_input :112-121)."""
+    (magicdrive/networks/blocks.py:144-238; the three modes of _construct_attn_input :106-142)."""
     x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x), None, heads)
     if (p + ".attn2.to_q.weight") in sd:  # absent only in the cross_attention_dim=None known-answer test
         x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), ctx, heads)
@@ -117,33 +117,44 @@ def transformer_block(sd: SD, p: str, x, ctx, heads, multiview: bool, neighbors=
         h = _ln(sd, p + ".norm4", x)
         h = h.view(-1, n_cam, *h.shape[1:])  # (b, n, L, C)
         B = h.shape[0]
-        q_in, kv_in, cam_order = [], [], []
-        for key, values in neighbors.items():
-            for value in values:
-                q_in.append(h[:, key])
-                kv_in.append(h[:, value])
-                cam_order += [key] * B
-        q_in, kv_in = torch.cat(q_in, 0), torch.cat(kv_in, 0)
-        cam_order = torch.tensor(cam_order)
-        raw = attention(sd, p + ".attn4", q_in, kv_in, heads)
-        out = torch.zeros_like(h)
-        for cam_i in range(n_cam):
-            sel = raw[cam_order == cam_i]  # (n_pairs*B, L, C), pair-major
-            out[:, cam_i] = sel.view(-1, B, *sel.shape[1:]).sum(0)
-        out = out.view(-1, *out.shape[2:])
+        if attn_type == "self":  # blocks.py:134-138, 209-211: one attention over the tokens of all views of a scene
+            raw = attention(sd, p + ".attn4", h.reshape(B, -1, h.shape[-1]), None, heads)
+            out = raw.view(B, n_cam, -1, raw.shape[-1])
+        else:
+            q_in, kv_in, cam_order = [], [], []
+            for key, values in neighbors.items():
+                if attn_type == "add":  # :112-121 one (query view, neighbour) pair per attention batch entry
+                    for value in values:
+                        q_in.append(h[:, key])
+                        kv_in.append(h[:, value])
+                        cam_order += [key] * B
+                elif attn_type == "concat":  # :122-133 the neighbours' tokens concatenated along the key axis
+                    q_in.append(h[:, key])
+                    kv_in.append(torch.cat([h[:, value] for value in values], dim=1))
+                    cam_order += [key] * B
+                else:
+                    raise NotImplementedError(f"Unknown type: {attn_type}")
+            q_in, kv_in = torch.cat(q_in, 0), torch.cat(kv_in, 0)
+            cam_order = torch.tensor(cam_order)
+            raw = attention(sd, p + ".attn4", q_in, kv_in, heads)
+            out = torch.zeros_like(h)
+            for cam_i in range(n_cam):
+                sel = raw[cam_order == cam_i]  # (n_pairs*B, L, C), pair-major
+                out[:, cam_i] = sel.view(-1, B, *sel.shape[1:]).sum(0)
+        out = out.reshape(-1, *out.shape[2:])
         x = x + _lin(sd, p + ".connector", out)
     x = x + feed_forward(sd, p + ".ff", _ln(sd, p + ".norm3", x))
     return x
 
 
-def transformer_2d(sd: SD, p: str, x, ctx, heads, multiview, neighbors=None, groups=32):
+def transformer_2d(sd: SD, p: str, x, ctx, heads, multiview, neighbors=None, groups=32, attn_type: str = "add"):
     """Transformer2DModel.forward, diffusers/models/transformer_2d.py:276-315 (conv projections, GN eps 1e-6)."""
     b, c, hh, ww = x.shape
     res = x
     h = F.group_norm(x, groups, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
     h = _conv(sd, p + ".proj_in", h, padding=0)
     h = h.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
-    h = transformer_block(sd, p + ".transformer_blocks.0", h, ctx, heads, multiview, neighbors)
+    h = transformer_block(sd, p + ".transformer_blocks.0", h, ctx, heads, multiview, neighbors, attn_type)
     h = h.reshape(b, hh, ww, c).permute(0, 3, 1, 2).contiguous()
     return _conv(sd, p + ".proj_out", h, padding=0) + res
 
@@ -157,19 +168,20 @@ def upsample(sd: SD, p: str, x, size):
 # ---------------------------------------------------------------------------------------------- networks
 def _encoder(sd, cfg, sample, emb, ctx, multiview, neighbors):
     g, eps = cfg.norm_num_groups, cfg.norm_eps
+    at = getattr(cfg, "neighboring_attn_type", "add")
     skips = [sample]
     for blk in arch.down_blocks(cfg, multiview):
         for rs, tr in blk.layers:
             sample = resnet_block(sd, rs.prefix, sample, emb, g, eps)
             if tr is not None:
-                sample = transformer_2d(sd, tr.prefix, sample, ctx, tr.heads, multiview, neighbors, g)
+                sample = transformer_2d(sd, tr.prefix, sample, ctx, tr.heads, multiview, neighbors, g, at)
             skips.append(sample)
         if blk.sampler is not None:
             sample = _conv(sd, blk.sampler.prefix, sample, stride=2, padding=1)
             skips.append(sample)
     r0, tr, r1 = arch.mid_block(cfg, multiview)
     sample = resnet_block(sd, r0.prefix, sample, emb, g, eps)
-    sample = transformer_2d(sd, tr.prefix, sample, ctx, tr.heads, multiview, neighbors, g)
+    sample = transformer_2d(sd, tr.prefix, sample, ctx, tr.heads, multiview, neighbors, g, at)
     sample = resnet_block(sd, r1.prefix, sample, emb, g, eps)
     return sample, skips
 
@@ -197,7 +209,7 @@ def unet_forward(sd: SD, cfg: arch.UNetConfig, sample, timestep, encoder_hidden_
             sample = torch.cat([sample, res.pop()], dim=1)
             sample = resnet_block(sd, rs.prefix, sample, emb, g, eps)
             if tr is not None:
-                sample = transformer_2d(sd, tr.prefix, sample, encoder_hidden_states, tr.heads, mv, nb, g)
+                sample = transformer_2d(sd, tr.prefix, sample, encoder_hidden_states, tr.heads, mv, nb, g, cfg.neighboring_attn_type)
         if blk.sampler is not None:
             sample = upsample(sd, blk.sampler.prefix, sample, skips[-1].shape[2:])
     sample = F.silu(F.group_norm(sample, g, sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], eps))

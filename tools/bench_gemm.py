@@ -77,7 +77,7 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
         live = [i for i in range(160) if tr[i, 0] != 0]
         t0 = min(int(tr[i, 0]) for i in live)
         names = ["entry", "setup", "tma_end", "mma_end", "aux_stores_issued", "aux_drained", "epi_end", "mma_tile0", "epi_tile0",
-                 "pre_sync", "exit"]
+                 "pre_sync", "exit", "bar_init", "tmem_alloc", "cluster_sync", "first_full"]
         print(f"{name}: {len(live)} CTAs; ns since the first CTA's entry; kernel span {max(int(tr[i, 10]) for i in live) - t0} ns")
         dur = sorted(live, key=lambda i: int(tr[i, 10]))
         for cta in [live[0], live[1], dur[len(dur) // 2], dur[-2], dur[-1]]:
