@@ -48,6 +48,7 @@ def parse():
                     help="sampler fused into the step: ddim (BASELINE.json configs: 50-step DDIM) or unipc (the reference's default)")
     ap.add_argument("--cfg-streams", action="store_true",
                     help="opt-in: run the unconditional / conditional guidance halves as two concurrent graph branches")
+    ap.add_argument("--no-hires", action="store_true", help="skip the configs[3] (424x800) sub-record of the default run")
     ap.add_argument("--no-decode", action="store_true",
                     help="skip timing the VAE decode of the scene's 6 views (SURVEY.md section 8 f2, reported as vae_decode)")
     ap.add_argument("--shard", default="scenes", choices=["scenes", "views"],
@@ -440,6 +441,36 @@ def main():
                                        "hoisted = attn2 K/V projections, part of the algorithmic figure but computed once per "
                                        "call instead of every step; executed = tensor-core FLOPs the step actually launches"}}
 
+    # ---- BASELINE.json configs[3]: the same networks at 424x800 (53x100 latents, 400x400 BEV map), a sub-record of the default line
+    hires = None
+    if args.res == "224x400" and not args.no_hires and not by_views and n_gpus == 1:
+        import copy
+        a3 = copy.copy(args)
+        a3.res = "424x800"
+        inp3, h3, w3 = make_inputs(a3, rank)
+        pipe.release_graph()
+        pipe3 = BEVControlNetDenoiser(un, cn, use_cuda_graph=not args.no_graph, overlap_controlnet=not args.no_overlap,
+                                      scheduler=args.scheduler)
+        st3 = pipe3.prepare(inp3["latents"], inp3["prompt_embeds"], inp3["negative_prompt_embeds"], inp3["camera_param"],
+                            inp3["bboxes_3d_data"], inp3["bev_map"], guidance_scale=2.0)
+        pipe3.set_schedule(st3, 50)
+        for i in range(3):
+            pipe3.run_steps(st3, i, i + 1)
+        barrier()
+        e0.record()
+        n3 = 8
+        for i in range(n3):
+            pipe3.run_steps(st3, 3 + i, 4 + i)
+        e1.record()
+        barrier()
+        ms3 = e0.elapsed_time(e1) / n3
+        hires = {"workload": workload_config(a3, sharding)["workload"].replace("configs[2]", "configs[3]"), "latent_hw": [h3, w3],
+                 "ms_per_step": ms3, "value": args.scenes / (ms3 * 1e-3), "unit": "scene-steps/s", "steps": n3, "warmup": 3,
+                 "whole_step_tflops": TFLOP_PER_SCENE_STEP_CFG["424x800"] * args.scenes / (ms3 * 1e-3)}
+        pipe3.release_graph()
+        del pipe3, st3
+        torch.cuda.empty_cache()
+
     vae_decode = None
     if not args.no_decode and not by_views:
         from magicdrive_b200.models import AutoencoderKL
@@ -525,6 +556,8 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
                 "options": {"cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap,
                             "cfg_streams": bool(args.cfg_streams)}}
+        if hires is not None:
+            line["configs3_424x800"] = hires
         if vae_decode is not None:
             line["vae_decode"] = vae_decode
         if strong is not None:

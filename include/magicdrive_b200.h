@@ -149,6 +149,10 @@ int mdb_add(const void* a, const void* b, void* out, long long n, void* stream);
 
 /* Nearest-neighbour resize NHWC, src index = floor(dst * in / out) (resnet.py:156-159). */
 int mdb_upsample_nearest(const void* x, int n, int h, int w, int c, void* out, int ho, int wo, void* stream);
+/* nn.AdaptiveAvgPool2d((ho, wo)) over an NHWC fp32 map, optionally followed by SiLU: the pooling block of
+ * BEVControlNetConditioningEmbeddingPlus (magicdrive/networks/map_embedder.py:118, forward :66-76 applies SiLU after every
+ * block, the pool included).  Step-invariant (once per scene). */
+int mdb_adaptive_avgpool(const float* x, int n, int h, int w, int c, float* out, int ho, int wo, int silu, void* stream);
 
 /* Skinny linear for tiny M (time embedding MLP, time_emb_proj, camera / box encoders):
  * out[m, n] = act(in)[m, :] . W[n, :] + b[n], W bf16 [n, k] (ldw), in/out fp32.  pre_silu applies SiLU to the input,

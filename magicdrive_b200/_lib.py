@@ -52,6 +52,7 @@ SIGNATURES = {
     "mdb_attention_debug_trace": (_i, [_vp]),
     "mdb_add": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "mdb_upsample_nearest": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "mdb_adaptive_avgpool": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "mdb_linear_small": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp]),
     "mdb_timestep_embedding": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "mdb_fourier_embed": (_i, [_vp, _ll, _i, _i, _vp, _vp]),

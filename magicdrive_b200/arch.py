@@ -69,6 +69,9 @@ class ControlNetConfig:
     camera_out_dim: int = 768
     map_size: Tuple[int, int, int] = (8, 200, 200)
     conditioning_embedding_out_channels: Tuple[int, ...] = (16, 32, 96, 256)
+    # map_embedder_cls BEVControlNetConditioningEmbeddingPlus (configs/exp/272x736.yaml:16-22): (h, w) of its AdaptiveAvgPool2d,
+    # i.e. the latent grid the BEV-map embedding is pooled to; None = the plain BEVControlNetConditioningEmbedding
+    map_embedding_size: Optional[Tuple[int, int]] = None
     cam_num_freqs: int = 4
     # bbox embedder (ContinuousBBoxWithTextEmbedding, mode all-xyz, minmax_normalize False)
     bbox_n_classes: int = 10
@@ -263,16 +266,24 @@ def unet_param_shapes(cfg: UNetConfig) -> "OrderedDict[str, tuple]":
 
 
 def map_encoder_layers(cfg: ControlNetConfig):
-    """(name, cin, cout, stride(h,w), pad(h,w)) of BEVControlNetConditioningEmbedding (map_embedder.py:28-64)."""
+    """(name, cin, cout, stride(h,w), pad(h,w)) of BEVControlNetConditioningEmbedding (map_embedder.py:28-64) or, with
+    cfg.map_embedding_size set, of BEVControlNetConditioningEmbeddingPlus (:79-126: all pads 1, first strided block stride 1,
+    and an AdaptiveAvgPool2d(cfg.map_embedding_size) as `blocks.{last}` ahead of conv_out -- it has no parameters and is
+    not listed here; engine / oracle insert it)."""
     ch = cfg.conditioning_embedding_out_channels
+    plus = cfg.map_embedding_size is not None
     layers = [("controlnet_cond_embedding.conv_in", cfg.map_size[0], ch[0], (1, 1), (1, 1))]
     bi = 0
     for i in range(len(ch) - 2):
         layers.append((f"controlnet_cond_embedding.blocks.{bi}", ch[i], ch[i], (1, 1), (1, 1)))
-        layers.append((f"controlnet_cond_embedding.blocks.{bi + 1}", ch[i], ch[i + 1], (2, 2), (2, 1)))
+        if plus:
+            st = (1, 1) if i == 0 else (2, 2)
+            layers.append((f"controlnet_cond_embedding.blocks.{bi + 1}", ch[i], ch[i + 1], st, (1, 1)))
+        else:
+            layers.append((f"controlnet_cond_embedding.blocks.{bi + 1}", ch[i], ch[i + 1], (2, 2), (2, 1)))
         bi += 2
-    layers.append((f"controlnet_cond_embedding.blocks.{bi}", ch[-2], ch[-2], (1, 1), (2, 1)))
-    layers.append((f"controlnet_cond_embedding.blocks.{bi + 1}", ch[-2], ch[-1], (2, 1), (2, 1)))
+    layers.append((f"controlnet_cond_embedding.blocks.{bi}", ch[-2], ch[-2], (1, 1), (1, 1) if plus else (2, 1)))
+    layers.append((f"controlnet_cond_embedding.blocks.{bi + 1}", ch[-2], ch[-1], (2, 1), (1, 1) if plus else (2, 1)))
     layers.append(("controlnet_cond_embedding.conv_out", ch[-1], cfg.block_out_channels[0], (1, 1), (1, 1)))
     return layers
 

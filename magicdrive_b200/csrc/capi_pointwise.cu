@@ -44,6 +44,27 @@ __global__ void upsample_nearest_kernel(const uint4* __restrict__ x, int n, int 
   o[i] = __ldg(x + ((static_cast<long long>(img) * h + ih) * w + iw) * c8 + cv);
 }
 
+// AdaptiveAvgPool2d over NHWC fp32 (+ optional SiLU): window [floor(o * in / out), ceil((o + 1) * in / out)) like ATen
+__global__ void adaptive_avgpool_kernel(const float* __restrict__ x, int n, int h, int w, int c, float* __restrict__ o, int ho,
+                                        int wo, int silu) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * ho * wo * c;
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % c);
+  long long p = i / c;
+  const int ow = static_cast<int>(p % wo);
+  p /= wo;
+  const int oh = static_cast<int>(p % ho);
+  const int img = static_cast<int>(p / ho);
+  const int h0 = (oh * h) / ho, h1 = ((oh + 1) * h + ho - 1) / ho;
+  const int w0 = (ow * w) / wo, w1 = ((ow + 1) * w + wo - 1) / wo;
+  float acc = 0.f;
+  for (int ih = h0; ih < h1; ++ih)
+    for (int iw = w0; iw < w1; ++iw) acc += __ldg(x + ((static_cast<long long>(img) * h + ih) * w + iw) * c + ch);
+  acc /= static_cast<float>((h1 - h0) * (w1 - w0));
+  o[i] = silu ? acc / (1.0f + expf(-acc)) : acc;
+}
+
 template <typename T>
 __device__ __forceinline__ float ldf(const T* p);
 template <>
@@ -324,6 +345,15 @@ extern "C" int mdb_upsample_nearest(const void* x, int n, int h, int w, int c, v
   upsample_nearest_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), n, h, w, c / 8, static_cast<uint4*>(out), ho, wo);
   MDB_CHECK_LAUNCH("upsample_nearest_kernel");
+  return MDB_OK;
+}
+
+extern "C" int mdb_adaptive_avgpool(const float* x, int n, int h, int w, int c, float* out, int ho, int wo, int silu, void* stream) {
+  if (!x || !out) return set_error(MDB_ERR_INVALID, "mdb_adaptive_avgpool: null pointer");
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || ho <= 0 || wo <= 0) return set_error(MDB_ERR_INVALID, "mdb_adaptive_avgpool: bad shape");
+  const long long total = static_cast<long long>(n) * ho * wo * c;
+  adaptive_avgpool_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, h, w, c, out, ho, wo, silu);
+  MDB_CHECK_LAUNCH("adaptive_avgpool_kernel");
   return MDB_OK;
 }
 

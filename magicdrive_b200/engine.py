@@ -532,6 +532,11 @@ class ControlNetEngine(_Net):
         for i, (name, ci, co, stride, pad) in enumerate(layers):
             wd, bias = self.W.conv_direct(name)
             last = i == len(layers) - 1
+            if last and self.cfg.map_embedding_size is not None:
+                # BEVControlNetConditioningEmbeddingPlus: AdaptiveAvgPool2d + SiLU ahead of conv_out (map_embedder.py:118, 70-72)
+                ho, wo = self.cfg.map_embedding_size
+                x = ops.adaptive_avgpool(x, n, h, w, ci, ho, wo, silu=True)
+                h, w = ho, wo
             x = ops.conv_direct(x, wd, bias, n=n, h=h, w=w, cin=ci, cout=co, k=3, stride=stride, pad=pad, silu=not last,
                                 out_f32=not last)
             h, w = x.shape[1], x.shape[2]
@@ -539,7 +544,7 @@ class ControlNetEngine(_Net):
 
     # ---------------------------------------------------------------- per-step
     def forward(self, latents_pad, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view: torch.Tensor,
-                conditioning_scale: float = 1.0, temb_all: Optional[torch.Tensor] = None):
+                conditioning_scale=1.0, temb_all: Optional[torch.Tensor] = None):
         """latents [n*h*w, 64] bf16 channel-padded (n = scenes*views); t_f32 [n]; map_emb_per_view [n, h, w, 320] bf16.
         Returns (12 + 1 residual maps as [pixels, C] bf16 tensors)."""
         x, skips = self.trunk(latents_pad, n, h, w, t_f32, ctx_kv, lc, map_emb_per_view, temb_all)
@@ -553,23 +558,26 @@ class ControlNetEngine(_Net):
         x = self.conv_in(latents_pad, n, h, w, residual=map_emb_per_view)
         return self.encoder(x, temb_all, ctx_kv, lc)
 
-    def residuals(self, skips, x, conditioning_scale: float = 1.0, add_to=None, add_to_mid=None, before=None):
+    def residuals(self, skips, x, conditioning_scale=1.0, add_to=None, add_to_mid=None, before=None):
         """The 12 + 1 zero convolutions (unet_addon_rawbox.py:898-915).  With `add_to` / `add_to_mid` (the UNet's own skip
         tensors and mid output) every zero convolution takes that tensor as its epilogue residual and returns
         `unet_skip + scale * zero_conv(controlnet_skip)`: the additions of unet_2d_condition_multiview.py:479-497 ride the
         GEMM that produces the residual, which is then never written or re-read.  `before(i)` is called ahead of the
-        i-th launch (the pipeline waits there for the event of UNet skip i)."""
+        i-th launch (the pipeline waits there for the event of UNet skip i).  `conditioning_scale`: one factor, or a list of
+        len(skips) + 1 factors (guess_mode: torch.logspace(-1, 0, 13) * scale, unet_addon_rawbox.py:897-905)."""
+        scales = list(conditioning_scale) if isinstance(conditioning_scale, (list, tuple)) else [conditioning_scale] * (len(skips) + 1)
+        assert len(scales) == len(skips) + 1
         down = []
         for i, s in enumerate(skips):
             wz, bz = self.W.conv(f"controlnet_down_blocks.{i}")
             if before is not None:
                 before(i)
-            down.append(ops.linear(s.data, wz, bias=bz, out_scale=conditioning_scale,
+            down.append(ops.linear(s.data, wz, bias=bz, out_scale=float(scales[i]),
                                    residual=None if add_to is None else add_to[i]))
         wz, bz = self.W.conv("controlnet_mid_block")
         if before is not None:
             before(len(skips))
-        mid = ops.linear(x.data, wz, bias=bz, out_scale=conditioning_scale, residual=add_to_mid)
+        mid = ops.linear(x.data, wz, bias=bz, out_scale=float(scales[-1]), residual=add_to_mid)
         return down, mid
 
 

@@ -248,14 +248,26 @@ class BEVControlNetModel(_B200Module):
                          bbox_proj_dims=tuple(bep.get("proj_dims", (768, 512, 512, 768))))
         if known.get("conditioning_embedding_out_channels") is None:
             known.pop("conditioning_embedding_out_channels", None)
+        # map embedder class (unet_addon_rawbox.py:172-181): the default BEVControlNetConditioningEmbedding built from map_size,
+        # or BEVControlNetConditioningEmbeddingPlus built from map_embedder_param (configs/exp/272x736.yaml:16-22)
+        mcls, mpar = extra.get("map_embedder_cls"), dict(extra.get("map_embedder_param") or {})
+        if mcls is not None:
+            if str(mcls).rsplit(".", 1)[-1] != "BEVControlNetConditioningEmbeddingPlus":
+                raise ValueError(f"map_embedder_cls {mcls!r} is not implemented (BEVControlNetConditioningEmbedding[Plus] only)")
+            if "conditioning_embedding_size" not in mpar:
+                raise ValueError("BEVControlNetConditioningEmbeddingPlus needs map_embedder_param.conditioning_embedding_size")
+            known["map_embedding_size"] = tuple(int(v) for v in mpar["conditioning_embedding_size"])
+            known["map_size"] = tuple(mpar.get("conditioning_size", (25, 200, 200)))
+            known["conditioning_embedding_out_channels"] = tuple(mpar.get("block_out_channels", (16, 32, 96, 256)))
+            if mpar.get("conditioning_embedding_channels", known.get("block_out_channels", (320,))[0]) != \
+                    known.get("block_out_channels", (320,))[0]:
+                raise ValueError("conditioning_embedding_channels must equal block_out_channels[0]")
         if known.get("map_size") is None:
             known.pop("map_size", None)
         cfg = arch.ControlNetConfig(**known)
         extra.update(cam_embedder_param=cep, bbox_embedder_param=bep,
                      controlnet_conditioning_channel_order=extra.get("controlnet_conditioning_channel_order", "rgb"),
                      global_pool_conditions=extra.get("global_pool_conditions", False))
-        if extra.get("map_embedder_cls") not in (None,):
-            raise ValueError("custom map_embedder_cls is not implemented (BEVControlNetConditioningEmbedding only)")
         self._init_common(cfg, arch.controlnet_param_shapes(cfg), extra)
         # unconditional BEV map (unet_addon_rawbox.py:188-202): present (and a checkpoint key) only when configured
         um = extra.get("use_uncond_map")
@@ -368,9 +380,9 @@ class BEVControlNetModel(_B200Module):
                 encoder_hidden_states_uncond=None, conditioning_scale: float = 1.0, class_labels=None,
                 timestep_cond=None, attention_mask=None, cross_attention_kwargs=None, guess_mode: bool = False,
                 return_dict: bool = True, **kwargs):
-        if guess_mode:
-            raise NotImplementedError("guess_mode is not on the MagicDrive inference path (add_uncond_to_emb has a "
-                                      "latent bug in the reference: unet_addon_rawbox.py:684-702)")
+        # guess_mode: the 12 + 1 residuals are scaled by torch.logspace(-1, 0, 13) * conditioning_scale instead of one factor
+        # (unet_addon_rawbox.py:897-905).  Only the MODULE-level switch exists here: the reference pipeline's guess_mode + CFG
+        # branch calls add_uncond_to_emb, which has a latent bug (:684-702), so the denoiser does not offer it.
         if self.config.get("controlnet_conditioning_channel_order", "rgb") != "rgb":
             raise ValueError("only 'rgb' controlnet_conditioning_channel_order is supported")
         eng = self._get_engine(ControlNetEngine)
@@ -380,7 +392,10 @@ class BEVControlNetModel(_B200Module):
         t = _timesteps_f32(timestep, b, sample.device)
         if t.numel() == b and n_cam > 1:
             t = t.repeat_interleave(n_cam)  # 'b ... -> (b repeat) ...' (:840-841)
-        down, mid, skips, xm = eng.forward(x, b * n_cam, h, w, t, cond["kv"], cond["lc"], cond["map"], conditioning_scale)
+        n_res = len(arch.controlnet_residual_channels(self.arch_cfg)) + 1  # 12 down residuals + mid
+        scale = ([float(v) * float(conditioning_scale) for v in torch.logspace(-1, 0, n_res)] if guess_mode
+                 else float(conditioning_scale))
+        down, mid, skips, xm = eng.forward(x, b * n_cam, h, w, t, cond["kv"], cond["lc"], cond["map"], scale)
         dt = sample.dtype
         down_nchw = [ops.nhwc_to_nchw(d, s.n, s.c, s.h, s.w, F32).to(dt) for d, s in zip(down, skips)]
         mid_nchw = ops.nhwc_to_nchw(mid, xm.n, xm.c, xm.h, xm.w, F32).to(dt)

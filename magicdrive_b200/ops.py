@@ -318,6 +318,17 @@ def upsample_nearest(x, n, h, w, c, ho, wo):
     return out
 
 
+def adaptive_avgpool(x, n, h, w, c, ho, wo, silu=False):
+    """nn.AdaptiveAvgPool2d((ho, wo)) (+ SiLU) over an NHWC fp32 map [n, h, w, c] -> fp32 [n, ho, wo, c]."""
+    global _launches
+    _need_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    out = torch.empty((n, ho, wo, c), dtype=F32, device=x.device)
+    check(_lib.lib().mdb_adaptive_avgpool(_ptr(x), n, h, w, c, _ptr(out), ho, wo, int(silu), _stream()), "mdb_adaptive_avgpool")
+    _launches += 1
+    return out
+
+
 def linear_small(x, w, bias=None, pre_silu=False, post_silu=False):
     """x fp32 [m, k]; w bf16 [n, k]; returns fp32 [m, n]."""
     global _launches

@@ -243,11 +243,14 @@ def bbox_embed(sd: SD, cfg: arch.ControlNetConfig, bboxes, classes, masks):
 
 
 def map_encode(sd: SD, cfg: arch.ControlNetConfig, cond):
-    """BEVControlNetConditioningEmbedding.forward, magicdrive/networks/map_embedder.py:66-76."""
+    """BEVControlNetConditioningEmbedding.forward, magicdrive/networks/map_embedder.py:66-76; with cfg.map_embedding_size the
+    ...Plus variant (:79-126), whose last block is AdaptiveAvgPool2d and is followed by SiLU like every block."""
     layers = arch.map_encoder_layers(cfg)
     x = cond
     for name, _, _, stride, pad in layers[:-1]:
         x = F.silu(F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride=stride, padding=pad))
+    if cfg.map_embedding_size is not None:
+        x = F.silu(F.adaptive_avg_pool2d(x, tuple(cfg.map_embedding_size)))
     name = layers[-1][0]
     return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], padding=1)
 
@@ -279,9 +282,10 @@ def uncond_cam_param(sd: SD, cfg: arch.ControlNetConfig, batch, n_cam):
 
 
 def controlnet_forward(sd: SD, cfg: arch.ControlNetConfig, sample, timestep, camera_param, bboxes_3d_data,
-                       encoder_hidden_states, controlnet_cond, conditioning_scale=1.0):
+                       encoder_hidden_states, controlnet_cond, conditioning_scale=1.0, guess_mode=False):
     """BEVControlNetModel.forward (inference path), magicdrive/networks/unet_addon_rawbox.py:707-932.
-    sample (b, n, 4, h, w).  Returns (down residuals [list], mid residual, ctx (b*n, L, 768))."""
+    sample (b, n, 4, h, w).  Returns (down residuals [list], mid residual, ctx (b*n, L, 768)).
+    guess_mode: per-residual factors torch.logspace(-1, 0, 13) * conditioning_scale (:897-905)."""
     b, n_cam = sample.shape[:2]
     ctx = controlnet_context(sd, cfg, camera_param, bboxes_3d_data, encoder_hidden_states)
     t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep])
@@ -295,9 +299,11 @@ def controlnet_forward(sd: SD, cfg: arch.ControlNetConfig, sample, timestep, cam
     cond = controlnet_cond.repeat_interleave(n_cam, dim=0)
     x = _conv(sd, "conv_in", x) + map_encode(sd, cfg, cond)
     x, skips = _encoder(sd, cfg, x, emb, ctx, False, None)
-    down = [F.conv2d(s, sd[f"controlnet_down_blocks.{i}.weight"], sd[f"controlnet_down_blocks.{i}.bias"]) * conditioning_scale
+    scales = (torch.logspace(-1, 0, len(skips) + 1) * conditioning_scale if guess_mode
+              else torch.full((len(skips) + 1,), float(conditioning_scale)))
+    down = [F.conv2d(s, sd[f"controlnet_down_blocks.{i}.weight"], sd[f"controlnet_down_blocks.{i}.bias"]) * scales[i].to(s.dtype)
             for i, s in enumerate(skips)]
-    mid = F.conv2d(x, sd["controlnet_mid_block.weight"], sd["controlnet_mid_block.bias"]) * conditioning_scale
+    mid = F.conv2d(x, sd["controlnet_mid_block.weight"], sd["controlnet_mid_block.bias"]) * scales[-1].to(x.dtype)
     return down, mid, ctx
 
 

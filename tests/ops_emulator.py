@@ -153,6 +153,12 @@ def upsample_nearest(x, n, h, w, c, ho, wo):
     return xi[:, iy][:, :, ix].reshape(n * ho * wo, c).contiguous()
 
 
+def adaptive_avgpool(x, n, h, w, c, ho, wo, silu=False):
+    y = F.adaptive_avg_pool2d(x.float().reshape(n, h, w, c).permute(0, 3, 1, 2), (ho, wo))
+    y = F.silu(y) if silu else y
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
 def linear_small(x, w, bias=None, pre_silu=False, post_silu=False):
     h = F.silu(x.float()) if pre_silu else x.float()
     y = h @ w.float().t()
@@ -235,7 +241,7 @@ class workspace_slot:
         return False
 
 
-EMULATED = ["softmax_rows", "gemm_conv", "linear", "conv_direct", "groupnorm", "layernorm", "attention", "add", "upsample_nearest",
+EMULATED = ["softmax_rows", "gemm_conv", "linear", "conv_direct", "groupnorm", "layernorm", "attention", "add", "upsample_nearest", "adaptive_avgpool",
             "linear_small", "timestep_embedding", "fourier_embed", "nchw_to_nhwc", "nhwc_to_nchw", "f32_to_bf16",
             "pack_latents", "cfg_ddim_step", "cfg_unipc_step", "pin_views", "workspace_slot"]
 

@@ -124,6 +124,64 @@ def test_layernorm_fold_rounding_is_bf16_weight_noise(monkeypatch):
 
 
 @torch.no_grad()
+@pytest.mark.parametrize("attn_type", ["concat", "self"])
+def test_cross_view_attention_types_through_emulated_operators(emulated, attn_type):
+    """neighboring_attn_type 'concat' (one softmax over both neighbours' keys) and 'self' (one attention over all views' tokens),
+    blocks.py:122-138: the engine's gather / batch re-interpretation against the reference's own outputs."""
+    from dataclasses import replace
+    from tests.common import golden
+    g = golden("tiny_attn_types.pt")
+    ucfg = replace(tiny_configs()[0], neighboring_attn_type=attn_type)
+    usd = _bf16_exact(arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), g["seed"]))
+    un = models.UNet2DConditionModelMultiview(**asdict(ucfg))
+    un.load_state_dict(usd)
+    eps = un(g["sample"], torch.tensor(g["t"]), encoder_hidden_states=g["ctx"]).sample
+    ref = O.unet_forward(usd, ucfg, g["sample"], torch.tensor(g["t"]), g["ctx"])
+    assert eps.shape == ref.shape and rel_l2(eps, ref) < 3e-3, rel_l2(eps, ref)
+    assert rel_l2(eps, g["eps"][attn_type]) < 2e-2  # weights rounded to bf16-exact values here: loose against the fp32 fixture
+
+
+@torch.no_grad()
+def test_map_embedder_plus_through_emulated_operators(emulated):
+    """map_embedder_cls = ...BEVControlNetConditioningEmbeddingPlus with map_embedder_param, as configs/exp/272x736.yaml passes
+    them: layer strides / pads, the adaptive pooling block and its SiLU (map_embedder.py:79-126)."""
+    from tests.test_oracle_cpu import _map_plus_case
+    g, gf, ccfg, csd = _map_plus_case()
+    kw = {k: v for k, v in asdict(ccfg).items() if k not in ("map_embedding_size", "map_size", "conditioning_embedding_out_channels")}
+    cn = models.BEVControlNetModel(map_embedder_cls="magicdrive.networks.map_embedder.BEVControlNetConditioningEmbeddingPlus",
+                                   map_embedder_param=dict(conditioning_embedding_size=[10, 13], conditioning_size=[8, 52, 60],
+                                                           block_out_channels=[16, 32, 96, 256]), **kw)
+    assert cn.arch_cfg == ccfg
+    csd = _bf16_exact(csd)
+    cn.load_state_dict(csd)
+    inp = gf["inputs"]
+    lat5 = torch.stack([inp["latents"]] * 6, 1)[:1]
+    down, mid, _ = cn(lat5, torch.tensor([gf["t"]]), inp["camera_param"][:1], None, inp["prompt_embeds"][:1], g["bev_map"],
+                      return_dict=False)
+    d32, m32, _ = O.controlnet_forward(csd, ccfg, lat5, torch.tensor([gf["t"]]), inp["camera_param"][:1], None,
+                                       inp["prompt_embeds"][:1], g["bev_map"])
+    assert rel_l2(mid, m32) < 2e-5 and rel_l2(down[0], d32[0]) < 2e-5
+    with pytest.raises(ValueError):
+        models.BEVControlNetModel(map_embedder_cls="some.other.Embedder", **kw)
+
+
+@torch.no_grad()
+def test_guess_mode_residual_scales_through_emulated_operators(emulated):
+    """BEVControlNetModel.forward(guess_mode=True): per-residual out_scale of the zero convolutions (unet_addon_rawbox.py:897-905)."""
+    ucfg, ccfg = tiny_configs()
+    _, cn, _, csd = _modules(ucfg, ccfg, 31)
+    inp = synthetic_inputs(1, 6, 10, 13, n_box=4, map_hw=52, seed=8)
+    lat5 = torch.stack([inp["latents"]] * 6, 1)
+    t = torch.tensor([481])
+    down, mid, _ = cn(lat5, t, inp["camera_param"], inp["bboxes_3d_data"], inp["prompt_embeds"], inp["bev_map"],
+                      conditioning_scale=0.7, guess_mode=True, return_dict=False)
+    d32, m32, _ = O.controlnet_forward(csd, ccfg, lat5, t, inp["camera_param"], inp["bboxes_3d_data"], inp["prompt_embeds"],
+                                       inp["bev_map"], conditioning_scale=0.7, guess_mode=True)
+    for a, b in zip(down + [mid], d32 + [m32]):
+        assert a.shape == b.shape and rel_l2(a, b) < 2e-5
+
+
+@torch.no_grad()
 @pytest.mark.parametrize("scheduler,guidance,fused", [("ddim", 2.0, True), ("unipc", 2.0, True), ("ddim", 1.0, True),
                                                       ("ddim", 2.0, False)])
 def test_denoiser_through_emulated_operators_matches_the_oracle_loop(emulated, scheduler, guidance, fused):

@@ -266,3 +266,66 @@ def test_view_sharded_cross_view_attention_two_gpus():
                        capture_output=True, text=True, timeout=900, cwd=root)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and r.stdout.count("OK") >= 4
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("attn_type", ["concat", "self"])
+def test_cross_view_attention_types_vs_reference_fixture(cuda_lib, attn_type):
+    """neighboring_attn_type 'concat' / 'self' (magicdrive/networks/blocks.py:122-138, 209-211) on the GPU against the
+    reference's own forward (tests/golden/tiny_attn_types.pt) with the bf16 criterion of this file."""
+    from dataclasses import replace
+    g = golden("tiny_attn_types.pt")
+    ucfg = replace(tiny_configs()[0], neighboring_attn_type=attn_type)
+    usd = arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), g["seed"])
+    un = UNet2DConditionModelMultiview(**asdict(ucfg))
+    un.load_state_dict(usd)
+    un = un.to(DEV)
+    sample, ctx, t = g["sample"].to(DEV), g["ctx"].to(DEV), torch.tensor(g["t"], device=DEV)
+    eps = un(sample, t, encoder_hidden_states=ctx).sample
+    ub = {k: v.to(DEV, torch.bfloat16) for k, v in usd.items()}
+    yard = O.unet_forward(ub, ucfg, sample.bfloat16(), t, ctx.bfloat16())
+    _check(f"attn_type={attn_type} eps", eps, g["eps"][attn_type], yard)
+
+
+@torch.no_grad()
+def test_guess_mode_residual_scales_vs_reference_fixture(cuda_lib):
+    """BEVControlNetModel.forward(guess_mode=True, conditioning_scale=0.7) against the reference's residuals
+    (unet_addon_rawbox.py:897-905; tests/golden/tiny_attn_types.pt['guess_mode'])."""
+    g, gf = golden("tiny_attn_types.pt")["guess_mode"], golden("tiny_forward.pt")
+    ucfg, ccfg = tiny_configs()
+    usd, csd = tiny_state_dicts(gf["seed"])
+    _, cn = _models(ucfg, ccfg, usd, csd)
+    inp = to_dev(gf["inputs"], DEV)
+    lat5 = torch.stack([inp["latents"]] * 6, 1)
+    t = torch.tensor([gf["t"]], device=DEV)
+    down, mid, _ = cn(lat5, t, inp["camera_param"], inp["bboxes_3d_data"], inp["prompt_embeds"], inp["bev_map"],
+                      conditioning_scale=g["conditioning_scale"], guess_mode=True, return_dict=False)
+    cb = {k: v.to(DEV, torch.bfloat16) for k, v in csd.items()}
+    dt = torch.bfloat16
+    yd, ym, _ = O.controlnet_forward(cb, ccfg, lat5.to(dt), t, inp["camera_param"].to(dt), to_dev(inp["bboxes_3d_data"], DEV, dt),
+                                     inp["prompt_embeds"].to(dt), inp["bev_map"].to(dt), conditioning_scale=g["conditioning_scale"],
+                                     guess_mode=True)
+    for i, (a, b, c) in enumerate(zip(down + [mid], g["down"] + [g["mid"]], yd + [ym])):
+        _check(f"guess_mode residual[{i}]", a, b, c)
+
+
+@torch.no_grad()
+def test_map_embedder_plus_vs_reference_fixture(cuda_lib):
+    """BEVControlNetConditioningEmbeddingPlus (272x736 experiment's BEV-map encoder incl. mdb_adaptive_avgpool) against the
+    reference's mid / first down residual (tests/golden/tiny_attn_types.pt['map_plus'])."""
+    from tests.test_oracle_cpu import _map_plus_case
+    g, gf, ccfg, csd = _map_plus_case()
+    cn = BEVControlNetModel(**asdict(ccfg))
+    cn.load_state_dict(csd)
+    cn = cn.to(DEV)
+    inp = to_dev(gf["inputs"], DEV)
+    lat5 = torch.stack([inp["latents"]] * 6, 1)[:1]
+    t = torch.tensor([gf["t"]], device=DEV)
+    bev = g["bev_map"].to(DEV)
+    down, mid, _ = cn(lat5, t, inp["camera_param"][:1], None, inp["prompt_embeds"][:1], bev, return_dict=False)
+    cb = {k: v.to(DEV, torch.bfloat16) for k, v in csd.items()}
+    dt = torch.bfloat16
+    yd, ym, _ = O.controlnet_forward(cb, ccfg, lat5.to(dt), t, inp["camera_param"][:1].to(dt), None, inp["prompt_embeds"][:1].to(dt),
+                                     bev.to(dt))
+    _check("map_plus mid", mid, g["mid"], ym)
+    _check("map_plus down[0]", down[0], g["down0"], yd[0])

@@ -271,3 +271,56 @@ def test_oracle_vae_decode_reproduces_reference_fixture():
     cfg = arch.VaeConfig(block_out_channels=tuple(g["block_out_channels"]))
     sd = arch.synthetic_state_dict(arch.vae_decoder_param_shapes(cfg), g["seed"])
     torch.testing.assert_close(O.vae_decode(sd, cfg, g["z"]), g["sample"], rtol=1e-4, atol=1e-4)
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("attn_type", ["concat", "self"])
+def test_oracle_reproduces_reference_cross_view_attention_types(attn_type):
+    """neighboring_attn_type 'concat' / 'self' (magicdrive/networks/blocks.py:122-138, 209-211) against the reference's own
+    forward (oracle/make_golden_attn_types.py)."""
+    from dataclasses import replace
+    g = golden("tiny_attn_types.pt")
+    ucfg = replace(tiny_configs()[0], neighboring_attn_type=attn_type)
+    usd = arch.synthetic_state_dict(arch.unet_param_shapes(ucfg), g["seed"])
+    eps = O.unet_forward(usd, ucfg, g["sample"], torch.tensor(g["t"]), g["ctx"])
+    torch.testing.assert_close(eps, g["eps"][attn_type], rtol=1e-3, atol=1e-4)
+    other = "self" if attn_type == "concat" else "concat"
+    assert (eps - g["eps"][other]).abs().max() > 1e-2  # the modes do differ on this fixture
+
+
+@torch.no_grad()
+def test_oracle_reproduces_reference_guess_mode_residual_scales():
+    """guess_mode: residual i scaled by logspace(-1, 0, 13)[i] * conditioning_scale (unet_addon_rawbox.py:897-905)."""
+    g, gf = golden("tiny_attn_types.pt")["guess_mode"], golden("tiny_forward.pt")
+    _, ccfg = tiny_configs()
+    _, csd = tiny_state_dicts(gf["seed"])
+    inp = gf["inputs"]
+    lat5 = torch.stack([inp["latents"]] * 6, 1)
+    down, mid, _ = O.controlnet_forward(csd, ccfg, lat5, torch.tensor([gf["t"]]), inp["camera_param"], inp["bboxes_3d_data"],
+                                        inp["prompt_embeds"], inp["bev_map"], conditioning_scale=g["conditioning_scale"],
+                                        guess_mode=True)
+    for a, b in zip(down + [mid], g["down"] + [g["mid"]]):
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4 * max(1.0, b.abs().max().item()))
+
+
+def _map_plus_case():
+    from dataclasses import replace
+    g, gf = golden("tiny_attn_types.pt")["map_plus"], golden("tiny_forward.pt")
+    _, ccfg = tiny_configs()
+    ccfg = replace(ccfg, map_size=(8, 52, 60), map_embedding_size=(10, 13))
+    csd = arch.synthetic_state_dict(arch.controlnet_param_shapes(ccfg), g["seed"])
+    return g, gf, ccfg, csd
+
+
+@torch.no_grad()
+def test_oracle_reproduces_reference_map_embedder_plus():
+    """BEVControlNetConditioningEmbeddingPlus (map_embedder.py:79-126, the 272x736 experiment's map encoder): embedding and the
+    ControlNet residuals computed with it, against the reference's own outputs."""
+    g, gf, ccfg, csd = _map_plus_case()
+    torch.testing.assert_close(O.map_encode(csd, ccfg, g["bev_map"]), g["embedding"], rtol=1e-3, atol=1e-4)
+    inp = gf["inputs"]
+    lat5 = torch.stack([inp["latents"]] * 6, 1)[:1]
+    down, mid, _ = O.controlnet_forward(csd, ccfg, lat5, torch.tensor([gf["t"]]), inp["camera_param"][:1], None,
+                                        inp["prompt_embeds"][:1], g["bev_map"])
+    torch.testing.assert_close(mid, g["mid"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(down[0], g["down0"], rtol=1e-3, atol=1e-4)
