@@ -44,6 +44,9 @@ struct GemmParams3 {
 #ifndef MDB_EPI_GROUPS
 #define MDB_EPI_GROUPS 2
 #endif
+#ifndef MDB_PAIR_AHEAD
+#define MDB_PAIR_AHEAD 4  // staging boxes (and residual loads) prepared this many chunks ahead of the store cursor (A/B knob)
+#endif
 
 // ---- fp32 pairs in 64-bit registers: FFMA2 / FADD2 / FMUL2 (sm_100) halve the epilogue's instruction count
 __device__ __forceinline__ unsigned long long pk2(float a, float b) {
@@ -132,7 +135,7 @@ struct PairCfg {
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kNBuf = 7;               // 128-row x 32-column (64 B) staging boxes: residual in, result out
-  static constexpr int kAhead = 4;              // how many chunks ahead of the store cursor buffers are prepared
+  static constexpr int kAhead = MDB_PAIR_AHEAD;              // how many chunks ahead of the store cursor buffers are prepared
   static constexpr int kBufBytes = 128 * 64;
   static constexpr int kEpiGroups = MDB_EPI_GROUPS;  // groups of four epilogue warps (one warp per TMEM lane quarter)
   static constexpr int kEpiWarps = 4 * kEpiGroups;
