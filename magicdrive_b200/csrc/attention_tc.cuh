@@ -33,6 +33,8 @@ struct AttnTcParams {
   int n_sets;
   int n_src;
   float scale_log2;
+  int q_step;  // attention_tc2 (single S buffer) only: > 0 = the CTA walks the query tiles blockIdx.x, blockIdx.x + q_step, ... of its
+               // (batch, head) with the K/V tile loaded once (lk <= 128, n_sets == 1: the conditioning cross-attention); 0 = one tile
   long long* trace;  // debug (mdb_attention_debug_trace): clock64 stamps of CTA (0,0,0): [3 warps][16 iterations][8 points]
 };
 

@@ -13,6 +13,11 @@
 //     warps sharing an SM sub-partition drift apart and overlap their MUFU and non-MUFU phases.
 //   * P (bf16 pairs) is written over the S columns it was computed from (no separate P region).
 //   TMEM columns (DOUBLE_S): S0 [0,128)  S1 [128,256)  O_a [256,256+D16)  O_b [384,384+D16);  single: S [0,128) O_a 128 O_b 192
+//   * MULTI-Q mode (p.q_step > 0; single-S variant, lk <= 128, one K/V set: the text / camera / box cross-attention, 98 keys):
+//     the CTA keeps its one K/V tile in shared memory and walks several query tiles, so that barrier initialisation, TMEM
+//     allocation and the K/V load are paid once per 3-4 tiles instead of once per tile (one-tile CTAs ran at ~70 TFLOP/s:
+//     each spent ~6 us on a fixed prologue / load / store chain for 0.3 us of tensor work).  The three roles reuse the loop over
+//     K/V SETS: a "set" is then a query tile (own Q load, own output rows, no accumulation into the previous set's output).
 //   warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: softmax
 //   (TMEM lane quarter = warp & 3, key half = (warp - 2) >> 2).
 #pragma once
@@ -43,7 +48,7 @@ struct AttnTc2Cfg {
 
 constexpr float ATT_LAZY_LOG2 = 8.0f;  // raise the reference maximum only when it grows by more than 2^8
 
-template <int D, bool DOUBLE_S>
+template <int D, bool DOUBLE_S, bool MULTI_Q = false>
 __global__ void __launch_bounds__(AttnTc2Cfg<D, DOUBLE_S>::kThreads, AttnTc2Cfg<D, DOUBLE_S>::kMinCtas)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnKvMaps kvm,
                      const AttnTcParams p) {
@@ -64,13 +69,22 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* o_full = bars + 14;    // MMA -> softmax: last PV of a KV set complete
   uint64_t* o_free = bars + 15;    // softmax (8 warps) -> MMA: O of the finished set has been read
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* q_empty = bars + 17;   // multi-Q mode: MMA (QK^T complete) -> TMA: the Q tile may be replaced
   float* xm = reinterpret_cast<float*>(bars + 32);  // [2 halves][128 rows] running max
   float* xl = xm + 2 * ATT_BM;                      // [2 halves][128 rows] row sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * ATT_BM;
+  const int b = blockIdx.z, head = blockIdx.y;
   const int ntiles = (p.lk + ATT_BN - 1) / ATT_BN;
-  const int total_iters = ntiles * p.n_sets;
+  // multi-Q mode: the outer ("set") loop of every role runs over this CTA's query tiles instead of K/V sets
+  static_assert(!(MULTI_Q && DOUBLE_S), "multi-Q mode exists for the single-S variant only");
+  constexpr bool multi_q = MULTI_Q;  // its own instantiation: the one-tile kernel keeps its register budget (96 / thread)
+  const int nq_tiles = (p.lq + ATT_BM - 1) / ATT_BM;
+  const int q0 = blockIdx.x * ATT_BM;
+  int n_outer = p.n_sets;
+  if constexpr (MULTI_Q) n_outer = (nq_tiles - static_cast<int>(blockIdx.x) + p.q_step - 1) / p.q_step;
+  auto q0_of = [&](int o) { return (static_cast<int>(blockIdx.x) + o * p.q_step) * ATT_BM; };  // multi-Q only
+  const int total_iters = ntiles * n_outer;
   long long* const trace = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.trace : nullptr;
 #define MDB_ATRACE(slot, it_, k)                                                       \
   do {                                                                                 \
@@ -97,6 +111,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(pv_done, 1);
     mbar_init(o_full, 1);
     mbar_init(o_free, 8);
+    mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -113,12 +128,22 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, KD * TILE);
+      auto load_q = [&](int qq) {
+        mbar_arrive_expect_tx(q_full, KD * TILE);
 #pragma unroll
-      for (int c = 0; c < KD; ++c) tma_load_4d(&tmQ, q_full, smQ + c * TILE, c * 64, head, q0, b);
+        for (int c = 0; c < KD; ++c) tma_load_4d(&tmQ, q_full, smQ + c * TILE, c * 64, head, qq, b);
+      };
+      load_q(q0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int set = 0; set < p.n_sets; ++set) {
+      for (int set = 0; set < n_outer; ++set) {
+        if constexpr (MULTI_Q) {
+          if (set > 0) {  // next query tile once QK^T of the previous one has read Q; the K/V tile stays
+            mbar_wait(q_empty, static_cast<uint32_t>(set - 1) & 1u);
+            load_q(q0_of(set));
+            continue;
+          }
+        }
         const int kve = p.kv_index ? p.kv_index[b * p.n_sets + set] : b;
         const int kvb = kve & 0xffffff;
         const CUtensorMap* km = &kvm.k[kve >> 24];
@@ -142,11 +167,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN);            // Q K^T: both K-major
     constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, D16) | (1u << 16);  // P V: B (V) MN-major
-    mbar_wait(q_full, 0);
-    // S_i -> buffer i % NBUF, K from ring stage i % STAGES
+    if (!multi_q) mbar_wait(q_full, 0);
+    // S_i -> buffer i % NBUF, K from ring stage i % STAGES (multi-Q: the one K/V tile in stage 0, Q tile i)
     auto issue_qk = [&](int i) {
-      const int st = i % STAGES;
-      mbar_wait(&kv_full[st], static_cast<uint32_t>(i / STAGES) & 1u);
+      const int st = multi_q ? 0 : i % STAGES;
+      if (multi_q) {
+        mbar_wait(q_full, static_cast<uint32_t>(i) & 1u);
+        if (i == 0) mbar_wait(&kv_full[0], 0);
+      } else {
+        mbar_wait(&kv_full[st], static_cast<uint32_t>(i / STAGES) & 1u);
+      }
       tc_fence_after();
       if (elect_one()) {
         const uint32_t tmem_s = tmem_base + static_cast<uint32_t>(i % NBUF) * ATT_BN;
@@ -158,6 +188,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_bf16(tmem_s, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[i % NBUF]);
+        if (multi_q) umma_commit(q_empty);
       }
       __syncwarp();
     };
@@ -165,7 +196,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (NBUF == 2 && total_iters > 1) issue_qk(1);
     int j = 0, set = 0;
     for (int it = 0; it < total_iters; ++it) {
-      const int s = it % NBUF, st = it % STAGES;
+      const int s = it % NBUF, st = multi_q ? 0 : it % STAGES;
       MDB_ATRACE(0, it, 0);
       mbar_wait(&p_full[s], static_cast<uint32_t>(it / NBUF) & 1u);  // P_it written, S_it no longer read
       MDB_ATRACE(0, it, 1);
@@ -202,13 +233,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t tmem_acc = lane_base + (hlf ? Cfg::OB_COL : Cfg::OA_COL);  // this half's accumulator (all D16 columns)
-    const int qrow = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.lq + qrow) * p.ldo + head * D + hlf * HW;
     constexpr int NVALID = (D - HW >= HW) ? HW : (D - HW);  // valid output columns of half 1 (half 0 always has HW)
     const int nvalid = hlf ? NVALID : HW;
     const float sc = p.scale_log2;
     int it = 0;
-    for (int set = 0; set < p.n_sets; ++set) {
+    int qrow = q0 + row;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.lq + qrow) * p.ldo + head * D + hlf * HW;
+    for (int set = 0; set < n_outer; ++set) {
+      if constexpr (MULTI_Q) {
+        qrow = q0_of(set) + row;
+        orow = p.out + (static_cast<long long>(b) * p.lq + qrow) * p.ldo + head * D + hlf * HW;
+      }
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < ntiles; ++j, ++it) {
         const int s = it % NBUF;
@@ -363,7 +398,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(oa[i]) * wa + __uint_as_float(ob[i]) * wb;
-          if (set > 0) {
+          if (set > 0 && !multi_q) {
             const uint4 prev = *reinterpret_cast<const uint4*>(orow + c);
             const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
 #pragma unroll

@@ -55,9 +55,35 @@ bool make_kv_maps(mdb::AttnKvMaps* m, const KvSources& s, int d, int heads, int 
   return true;
 }
 
+int attn_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// Query tiles per CTA walk (AttnTcParams::q_step) for the single-S tc2 kernel when one K/V tile covers all keys: as many
+// CTAs as two per SM, each keeping its K/V tile and walking ~nq / gx query tiles.  0 = one tile per CTA.  MDB_ATTN_MULTIQ=0 disables (A/B).
+int multi_q_step(int b, int heads, int lq, int lk, int n_sets) {
+  if (lk > mdb::ATT_BN || n_sets != 1) return 0;
+  const char* e = getenv("MDB_ATTN_MULTIQ");
+  if (e && e[0] == '0') return 0;
+  const int nq = (lq + mdb::ATT_BM - 1) / mdb::ATT_BM;
+  const long long per_tile_ctas = static_cast<long long>(b) * heads;
+  const long long slots = 2LL * attn_num_sms();
+  if (per_tile_ctas * nq <= slots) return 0;  // everything is co-resident anyway
+  long long gx = slots / per_tile_ctas;
+  if (gx < 1) gx = 1;
+  if (gx >= nq) return 0;
+  return static_cast<int>(gx);
+}
+
 template <typename Cfg, typename Kernel>
 int launch_tc(Kernel kernel, const char* name, const void* q, int ldq, const KvSources& src, void* out, int ldo, int b, int heads,
-              int lq, int lk, int d, const int* kv_index, int n_sets, float scale, cudaStream_t st, bool* attr) {
+              int lq, int lk, int d, const int* kv_index, int n_sets, float scale, cudaStream_t st, bool* attr, bool allow_multi_q = false) {
   if (!*attr) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "%s smem attr: %s", name, cudaGetErrorString(e));
@@ -72,7 +98,8 @@ int launch_tc(Kernel kernel, const char* name, const void* q, int ldq, const KvS
   p.ldo = ldo, p.lq = lq, p.lk = lk, p.kv_index = kv_index, p.n_sets = n_sets, p.n_src = src.n;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
-  dim3 grid((lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
+  p.q_step = allow_multi_q ? multi_q_step(b, heads, lq, lk, n_sets) : 0;
+  dim3 grid(p.q_step > 0 ? p.q_step : (lq + mdb::ATT_BM - 1) / mdb::ATT_BM, heads, b);
   cudaError_t le = mdb::launch_pdl(kernel, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tq, kvm, p);
   if (le != cudaSuccess) return mdb::set_error(MDB_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(le));
   cudaError_t e2 = cudaGetLastError();
@@ -91,9 +118,16 @@ int launch_attention_tc(const void* q, int ldq, const KvSources& src, void* out,
 template <int D, bool DOUBLE_S>
 int launch_attention_tc2(const void* q, int ldq, const KvSources& src, void* out, int ldo, int b, int heads, int lq, int lk,
                          const int* kv_index, int n_sets, float scale, cudaStream_t st) {
+  if constexpr (!DOUBLE_S) {
+    if (multi_q_step(b, heads, lq, lk, n_sets) > 0) {  // one K/V tile, more query tiles than CTA slots: multi-Q instantiation
+      static bool attr_mq = false;
+      return launch_tc<mdb::AttnTc2Cfg<D, false>>(mdb::attention_tc2_kernel<D, false, true>, "attention_tc2_kernel<multi-Q>", q, ldq, src,
+                                                  out, ldo, b, heads, lq, lk, D, kv_index, n_sets, scale, st, &attr_mq, true);
+    }
+  }
   static bool attr = false;
-  return launch_tc<mdb::AttnTc2Cfg<D, DOUBLE_S>>(mdb::attention_tc2_kernel<D, DOUBLE_S>, "attention_tc2_kernel", q, ldq, src, out, ldo,
-                                                 b, heads, lq, lk, D, kv_index, n_sets, scale, st, &attr);
+  return launch_tc<mdb::AttnTc2Cfg<D, DOUBLE_S>>(mdb::attention_tc2_kernel<D, DOUBLE_S, false>, "attention_tc2_kernel", q, ldq, src, out,
+                                                 ldo, b, heads, lq, lk, D, kv_index, n_sets, scale, st, &attr, false);
 }
 
 // Which kernel generation serves a call: MDB_ATTN_KERNEL = tc2 | tc2d | tc (A/B switch, read per call).

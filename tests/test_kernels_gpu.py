@@ -217,6 +217,30 @@ def test_attention(cuda_lib, monkeypatch, d, heads, lq, lk, kernel):
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=5e-3)
 
 
+@pytest.mark.parametrize("b,heads,d,lq,lk", [(12, 8, 40, 1400, 98), (12, 8, 40, 1337, 128), (12, 8, 40, 1400, 40), (30, 2, 32, 1400, 77),
+                                             (30, 2, 64, 700, 98), (40, 8, 40, 300, 1)])
+def test_attention_multi_q_tiles_per_cta(cuda_lib, monkeypatch, b, heads, d, lq, lk):
+    """One K/V tile (lk <= 128) and more query tiles than CTA slots: the single-S kernel's multi-Q instantiation (a CTA keeps the
+    K/V tile and walks several query tiles) against fp32 torch and, bit for bit, against the one-tile-per-CTA kernel."""
+    monkeypatch.delenv("MDB_ATTN_KERNEL", raising=False)
+    g = torch.Generator(device="cuda").manual_seed(29)
+    c = heads * d
+    q = _bf(torch.randn(b * lq, c, device="cuda", generator=g))
+    k = _bf(torch.randn(b * lk, c, device="cuda", generator=g))
+    v = _bf(torch.randn(b * lk, c, device="cuda", generator=g))
+    scale = d ** -0.5
+    monkeypatch.setenv("MDB_ATTN_MULTIQ", "1")
+    out = ops.attention(q, k, v, b=b, heads=heads, lq=lq, lk=lk, d=d, ldq=c, ldk=c, ldv=c, scale=scale)
+    monkeypatch.setenv("MDB_ATTN_MULTIQ", "0")
+    one = ops.attention(q, k, v, b=b, heads=heads, lq=lq, lk=lk, d=d, ldq=c, ldk=c, ldv=c, scale=scale)
+    qh = q.float().reshape(b, lq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(b, lk, heads, d).transpose(1, 2)
+    vh = v.float().reshape(b, lk, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(b * lq, c)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=5e-3)
+    assert torch.equal(out, one)
+
+
 @pytest.mark.parametrize("kernel", ATTN_KERNELS)
 @pytest.mark.parametrize("d,heads", [(40, 8), (80, 4)])
 @pytest.mark.parametrize("lq,lk", [(300, 700), (1400, 1400)])
