@@ -1,4 +1,4 @@
-"""profiles/traffic_rN.json from an ncu capture (-k regex:gemm_tc2_kernel, default --cache-control all so every replay
+"""profiles/traffic_rN.json from an ncu capture (-k regex:gemm_, default --cache-control all so every replay
 pass starts from a flushed L2) of one denoising step: average DRAM bytes (read + write) and duration per launch of the
 dominant kernel.  usage: traffic_from_ncu.py report.ncu-rep out.json ["note"]"""
 import csv
@@ -20,7 +20,7 @@ def col(name):
 
 rd, wr, dur = col("dram__bytes_read.sum"), col("dram__bytes_write.sum"), col("gpu__time_duration.sum")
 n = len(data)
-res = {"kernel": "gemm_tc2_kernel (all instantiations)", "launches_profiled": n,
+res = {"kernel": "gemm_pair_kernel + gemm_tc2_kernel (tcgen05 GEMM / implicit-GEMM conv, all launches of one denoising step)", "launches_profiled": n,
        "dram_bytes_per_launch": (sum(rd) + sum(wr)) / n, "dram_read_bytes_profiled": sum(rd), "dram_write_bytes_profiled": sum(wr),
        "avg_us_per_launch_under_ncu": sum(dur) / n, "source": rep,
        "note": sys.argv[3] if len(sys.argv) > 3 else ""}
