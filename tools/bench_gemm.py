@@ -45,6 +45,7 @@ ap.add_argument("--bn", type=int, default=0)
 ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--trace", action="store_true", help="print per-CTA clock64 phase stamps of the persistent kernel")
 ap.add_argument("--warm", action="store_true", help="no L2 flush between reps: operands L2-resident, like activations inside a step")
+ap.add_argument("--inner", type=int, default=1, help="launches between one pair of events (the event clock ticks in ~2 us steps)")
 ap.add_argument("--profile", action="store_true", help="one launch per shape between cudaProfilerStart/Stop (for ncu)")
 args = ap.parse_args()
 dev = "cuda"
@@ -120,10 +121,11 @@ for name, n, h, w, ci, co, taps, res, geglu in SHAPES:
             torch.cuda._sleep(400000)  # ~0.2 ms spin: the launch below is enqueued before the GPU gets to it (no host-bound gap)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.gemm_conv(x, wt, **kw)
+        for _ in range(args.inner):
+            ops.gemm_conv(x, wt, **kw)
         e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
-    us = tot / args.reps * 1e3
+    us = tot / args.reps / args.inner * 1e3
     fl = 2.0 * pix * co * taps * taps * ci
     print(f"{name:32s} {us:8.1f} {fl / us / 1e6:8.1f}")

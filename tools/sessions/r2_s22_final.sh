@@ -19,6 +19,7 @@ timeout 900 ncu --profile-from-start off --set full --import-source on --clock-c
    -k regex:gemm_pair --launch-skip 30 -c 24 -o $O/prof_pair python tools/profile_step.py --workload full > $O/ncu_pair.log 2>&1
 timeout 600 ncu --profile-from-start off --set full --import-source on --clock-control none --cache-control none \
    -k regex:attention_tc2 -c 6 -o $O/prof_attn python tools/profile_step.py --workload full > $O/ncu_attn.log 2>&1
+timeout 200 python tools/time_prepare.py > $O/time_prepare.txt 2>&1
 tail -n 6 $O/pytest_gpu.log; tail -3 $O/bench_default.err; head -12 $O/shape_times.txt; head -22 $O/launches_step.summary.txt; cat $O/traffic.log | cut -c1-600
 python -c "
 import json
