@@ -98,7 +98,8 @@ int mdb_gemm_conv_stats_parts(const mdb_gemm_desc* d);
 
 /* Direct (CUDA-core) convolution for tiny channel counts: conv_in 4->320 (unet_2d_condition.py:231),
  * conv_out 320->4 (:503), BEV map encoder (magicdrive/networks/map_embedder.py:66-76).
- * x: [n, h, w, cin] bf16 or fp32; w: fp32 [cout, kh, kw, cin]; out bf16/fp32 [n, ho, wo, cout] (+= residual). */
+ * x: [n, h, w, cin] bf16 or fp32; w: fp32 [kh, kw, cin, cout] (output channel innermost: coalesced across a warp);
+ * out bf16/fp32 [n, ho, wo, cout] (+= residual). */
 int mdb_conv_direct(const void* x, int x_is_f32, int n, int h, int w, int cin, const float* wgt, const float* bias,
                     int cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int ho, int wo,
                     int silu, const void* residual, void* out, int out_is_f32, void* stream);

@@ -217,7 +217,10 @@ __global__ void linear_small_kernel(const float* __restrict__ in, int m, int k, 
   }
 }
 
-// Direct convolution, one thread per output element, fp32 accumulate.
+// Direct convolution, one thread per output element (output channel fastest), fp32 accumulate.  Weights are [kh][kw][cin][cout]:
+// the threads of a warp (consecutive output channels of one pixel) read consecutive weights and broadcast-read the same input
+// value.  (With [cout][kh][kw][cin] weights every lane walked its own row, 32 sectors per load: the BEV-map encoder took
+// 12.9 ms of the 15.3 ms a re-conditioning call costs, profiles/time_prepare_r2.txt.)
 template <typename TI>
 __global__ void conv_direct_kernel(const TI* __restrict__ x, int n, int h, int w, int cin, const float* __restrict__ wgt,
                                    const float* __restrict__ bias, int cout, int kh, int kw, int sh, int sw, int ph,
@@ -240,8 +243,9 @@ __global__ void conv_direct_kernel(const TI* __restrict__ x, int n, int h, int w
       const int iw = ow * sw + s - pw;
       if (iw < 0 || iw >= w) continue;
       const TI* xp = x + ((static_cast<long long>(img) * h + ih) * w + iw) * cin;
-      const float* wp = wgt + ((static_cast<long long>(co) * kh + r) * kw + s) * cin;
-      for (int c = 0; c < cin; ++c) acc += ldf(xp + c) * __ldg(wp + c);
+      const float* wp = wgt + static_cast<long long>(r * kw + s) * cin * cout + co;
+#pragma unroll 4
+      for (int c = 0; c < cin; ++c) acc += ldf(xp + c) * __ldg(wp + static_cast<long long>(c) * cout);
     }
   }
   if (silu) acc = silu_f(acc);

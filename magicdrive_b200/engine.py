@@ -63,7 +63,7 @@ class _Weights:
 
     def conv_direct(self, p):
         if p + ".wd" not in self.t:
-            self.t[p + ".wd"] = _f32(self.raw(p + ".weight").float().permute(0, 2, 3, 1))
+            self.t[p + ".wd"] = _f32(self.raw(p + ".weight").float().permute(2, 3, 1, 0))  # [kh, kw, cin, cout]
             self.t[p + ".b"] = _f32(self.raw(p + ".bias"))
         return self.t[p + ".wd"], self.t[p + ".b"]
 
@@ -656,7 +656,7 @@ class VaeDecoderEngine:
         cfg, W = self.cfg, self.W
         key = ("pq", float(scale))
         if key not in W.t:  # 1x1 post_quant_conv with the latent scale folded into its weights
-            W.t[key] = (_f32(W.raw("post_quant_conv.weight").float().permute(0, 2, 3, 1) * scale), _f32(W.raw("post_quant_conv.bias")))
+            W.t[key] = (_f32(W.raw("post_quant_conv.weight").float().permute(2, 3, 1, 0) * scale), _f32(W.raw("post_quant_conv.bias")))
         wq, bq = W.t[key]
         lc = cfg.latent_channels
         x = ops.conv_direct(z_nhwc.reshape(n, h, w, lc), wq, bq, n=n, h=h, w=w, cin=lc, cout=lc, k=1, pad=(0, 0), out_f32=True)

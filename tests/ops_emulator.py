@@ -85,8 +85,8 @@ def linear(x, w, bias=None, residual=None, out=None, ldo=None, geglu=False, out_
 
 
 def conv_direct(x, wgt, bias, *, n, h, w, cin, cout, k, stride=(1, 1), pad=(1, 1), silu=False, residual=None, out_f32=False):
-    assert wgt.shape == (cout, k, k, cin)
-    y = F.conv2d(x.float().reshape(n, h, w, cin).permute(0, 3, 1, 2), wgt.float().permute(0, 3, 1, 2), bias.float(),
+    assert wgt.shape == (k, k, cin, cout)
+    y = F.conv2d(x.float().reshape(n, h, w, cin).permute(0, 3, 1, 2), wgt.float().permute(3, 2, 0, 1), bias.float(),
                  stride=stride, padding=pad)
     if silu:
         y = F.silu(y)

@@ -341,7 +341,7 @@ def test_conv_direct(cuda_lib):
     b = torch.randn(16, device="cuda", generator=g)
     ref = F.silu(F.conv2d(x, wt, b, stride=(2, 1), padding=(2, 1)))
     xh = x.permute(0, 2, 3, 1).contiguous()
-    out = ops.conv_direct(xh, wt.permute(0, 2, 3, 1).contiguous(), b, n=2, h=40, w=40, cin=8, cout=16, k=3, stride=(2, 1),
+    out = ops.conv_direct(xh, wt.permute(2, 3, 1, 0).contiguous(), b, n=2, h=40, w=40, cin=8, cout=16, k=3, stride=(2, 1),
                           pad=(2, 1), silu=True, out_f32=True)
     torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, atol=1e-4, rtol=1e-4)
 
