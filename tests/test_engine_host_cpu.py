@@ -47,9 +47,14 @@ def _modules(ucfg, ccfg, seed):
 
 
 @torch.no_grad()
-@pytest.mark.parametrize("layout,h,w,map_hw", [("tiny", 10, 13, 52), ("four_level", 28, 50, 200)])
+@pytest.mark.parametrize("layout,h,w,map_hw", [("tiny", 10, 13, 52), ("four_level", 28, 50, 200), ("four_level_272x736", 34, 92, 200)])
 def test_module_forwards_through_emulated_operators_match_the_oracle(emulated, layout, h, w, map_hw):
     ucfg, ccfg = tiny_configs() if layout == "tiny" else _four_level_configs()
+    if layout == "four_level_272x736":
+        # configs/exp/272x736.yaml: 34 x 92 latents (odd sizes down the pyramid: 17 x 46, 9 x 23, 5 x 12) and the ...Plus map
+        # encoder pooling the 200 x 200 BEV map to the latent grid
+        from dataclasses import replace
+        ccfg = replace(ccfg, map_embedding_size=(h, w))
     un, cn, usd, csd = _modules(ucfg, ccfg, 31)
     inp = synthetic_inputs(1, 6, h, w, n_box=4, map_hw=map_hw, seed=8)
     lat5 = torch.stack([inp["latents"]] * 6, 1)
