@@ -3,6 +3,9 @@
 torch is plumbing only: it owns device memory and the CUDA stream; every function here forwards raw pointers to
 `libmagicdrive_b200.so` and raises if the library / a CUDA device is unavailable (no CPU or eager fallback).
 Feature maps are NHWC bf16 ("channels innermost") everywhere; a token matrix [tokens, C] is the same layout.
+
+One process drives ONE device (the launch contract: one process per GPU): the module-level workspace slot / launch counter and the
+library's cached device attributes (SM count, per-kernel shared-memory opt-ins) are per process, not per device, and not thread-safe.
 """
 import ctypes as C
 import contextlib
