@@ -472,7 +472,7 @@ def main():
         torch.cuda.empty_cache()
 
     vae_decode = None
-    if not args.no_decode and not by_views:
+    if not args.no_decode and not by_views and world == 1:  # a sub-record of the single-GPU line only
         from magicdrive_b200.models import AutoencoderKL
         vae = AutoencoderKL(**asdict(arch.VaeConfig())).reset_parameters_synthetic(13).to(dev, torch.bfloat16)
         lat5 = pipe.latents_out(st) * 0.18215
